@@ -1,0 +1,95 @@
+"""ctypes binding of libbhray.so (include/bh_abi.h).  Fails loudly: there is no CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+_LIB = None
+
+
+class BhError(RuntimeError):
+    def __init__(self, code: int, text: str):
+        super().__init__(f"libbhray error {code}: {text}")
+        self.code = code
+
+
+class PassStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("ray_steps", "px_traced", "px_copied", "px_interp", "node_visits",
+                                          "tri_tests", "tex_samples", "rk_reject", "stack_overflow")]
+
+    def as_dict(self) -> dict:
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+class ModelInfo(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("point_count", "normal_count", "triangle_count", "nodes_used",
+                                         "max_depth", "leaf_count", "max_leaf_size")]
+
+    def as_dict(self) -> dict:
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+# every symbol include/bh_abi.h declares: name -> (restype, argtypes)
+_VP, _U32, _I32 = C.c_void_p, C.c_uint32, C.c_int32
+SYMBOLS = {
+    "bh_abi_version": (C.c_int, []),
+    "bh_last_error": (C.c_char_p, []),
+    "bh_ctx_create": (C.c_int, [C.c_int, C.POINTER(_VP)]),
+    "bh_ctx_destroy": (None, [_VP]),
+    "bh_ctx_set_texture": (C.c_int, [_VP, C.c_int, _VP, _U32, _U32]),
+    "bh_ctx_upload_models": (C.c_int, [_VP, _VP, C.c_size_t]),
+    "bh_ctx_upload_models_async": (C.c_int, [_VP, _VP, C.c_size_t, _VP]),
+    "bh_ctx_set_model_header": (C.c_int, [_VP, _U32, C.POINTER(C.c_float), _I32]),
+    "bh_ray_pipeline_create": (C.c_int, [_VP, _U32, _U32, _VP, C.POINTER(_VP)]),
+    "bh_ray_pipeline_destroy": (None, [_VP]),
+    "bh_ray_pipeline_set_tiling": (C.c_int, [_VP, _U32, _U32, _U32]),
+    "bh_ray_pipeline_local_rows": (_U32, [_VP]),
+    "bh_ray_pipeline_enable_aux": (C.c_int, [_VP, _U32]),
+    "bh_ray_pipeline_bind_output": (C.c_int, [_VP, _VP]),
+    "bh_ray_pipeline_pass": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
+    "bh_ray_pipeline_output": (_VP, [_VP]),
+    "bh_ray_pipeline_width": (_U32, [_VP]),
+    "bh_ray_pipeline_height": (_U32, [_VP]),
+    "bh_ray_pipeline_read": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
+    "bh_ray_pipeline_stats": (C.c_int, [_VP, C.POINTER(PassStats)]),
+    "bh_sky_pipeline_create": (C.c_int, [_VP, _VP, C.c_int, C.POINTER(_VP)]),
+    "bh_sky_pipeline_destroy": (None, [_VP]),
+    "bh_sky_pipeline_bind_output": (C.c_int, [_VP, _VP]),
+    "bh_sky_pipeline_pass": (C.c_int, [_VP, _VP]),
+    "bh_sky_pipeline_output": (_VP, [_VP]),
+    "bh_sky_pipeline_read": (C.c_int, [_VP, _VP]),
+    "bh_model_load_obj": (C.c_int, [C.c_char_p, _VP, C.POINTER(ModelInfo)]),
+    "bh_model_from_arrays": (C.c_int, [_VP, _I32, _VP, _I32, _VP, _I32, C.POINTER(C.c_float), _I32, _VP, C.POINTER(ModelInfo)]),
+    "bh_model_build_bvh": (C.c_int, [_VP, _I32, C.POINTER(ModelInfo)]),
+    "bh_ctx_math_probe": (C.c_int, [_VP, C.c_int, _VP, _VP, _VP, C.c_size_t]),
+}
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Loads libbhray.so from bhusie_b200/lib/ (built in-tree by bhusie_b200.build).  Raises if it is
+    missing and cannot be built — nothing in this package computes without it."""
+    global _LIB
+    if _LIB is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            _build.build_library()
+        lib = C.CDLL(path)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)          # AttributeError here == ABI/header mismatch
+            fn.restype = res
+            fn.argtypes = args
+        if lib.bh_abi_version() != 1:
+            raise RuntimeError("libbhray.so ABI version mismatch")
+        _LIB = lib
+    return _LIB
+
+
+def check(code: int) -> None:
+    if code != 0:
+        raise BhError(code, load().bh_last_error().decode(errors="replace"))

@@ -1,0 +1,456 @@
+// bh_abi.cu — the C ABI of libbhray.so (include/bh_abi.h): context, ray pass and sky pass objects.
+//
+// Mirrors the reference's pass-object triple new / pass / output_view
+// (src/renderer/pipelines/ray_pipeline.rs:36,297,301; sky_pipeline.rs:18,136,140) with plain
+// pointers and sizes.  pass() only ENQUEUES work on the caller's CUDA stream, the same contract as
+// recording into a wgpu ComputePass (execution starts at queue.submit, src/renderer/mod.rs:453).
+#include <cerrno>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "bh_device.h"
+
+namespace bh {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof g_error, fmt, ap);
+    va_end(ap);
+}
+
+static int cuda_fail(cudaError_t e, const char *what)
+{
+    set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    return (e == cudaErrorMemoryAllocation) ? BH_ERR_NOMEM
+         : (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice) ? BH_ERR_NODEV
+         : BH_ERR_CUDA;
+}
+
+#define BH_CUDA(call)                                             \
+    do {                                                          \
+        cudaError_t e_ = (call);                                  \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call);       \
+    } while (0)
+
+}  // namespace bh
+
+using namespace bh;
+
+static_assert(sizeof(bh_camera_uniform) == 32, "CameraUniform is 32 bytes (camera.rs:66-73)");
+static_assert(sizeof(bh_black_hole_uniform) == 132, "BlackHoleUniform is 132 bytes (blackhole.rs:37-51)");
+static_assert(sizeof(bh_ray_details) == 32, "RayDetails is 32 bytes (ray_pipeline.rs:3-14)");
+
+struct bh_ctx {
+    int device = 0;
+    int sm_count = 0;
+    uchar4 *tex[3] = { nullptr, nullptr, nullptr };
+    int tex_w[3] = { 0, 0, 0 }, tex_h[3] = { 0, 0, 0 };
+    unsigned char *models = nullptr;     // BH_MAX_MODELS * kModelStride
+    int models_uploaded = 0;
+};
+
+struct bh_ray_pipeline {
+    bh_ctx *ctx = nullptr;
+    uint32_t w = 0, h = 0;
+    const bh_ray_pipeline *prev = nullptr;
+    uint32_t band_rows = 0, rank = 0, n_ranks = 1, local_rows = 0;
+    float4 *own_out = nullptr;
+    size_t own_out_rows = 0;
+    float4 *bound_out = nullptr;
+    int32_t *aux_hit = nullptr;
+    uint32_t *aux_steps = nullptr;
+    uint8_t *aux_class = nullptr;
+    uint32_t aux_mask = 0;
+    unsigned long long *stats = nullptr;
+    unsigned int *work = nullptr;
+    unsigned int *queue = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool ran = false;
+    float4 *out() const { return bound_out ? bound_out : own_out; }
+};
+
+struct bh_sky_pipeline {
+    bh_ctx *ctx = nullptr;
+    const bh_ray_pipeline *prev = nullptr;
+    bh_sky_format format = BH_SKY_RGBA16F;
+    void *own_out = nullptr;
+    void *bound_out = nullptr;
+    unsigned long long *stats = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool ran = false;
+    void *out() const { return bound_out ? bound_out : own_out; }
+    size_t texel_bytes() const { return format == BH_SKY_RGBA32F ? 16 : 8; }
+};
+
+static uint32_t count_local_rows(uint32_t h, uint32_t band_rows, uint32_t rank, uint32_t n_ranks)
+{
+    if (n_ranks <= 1) return h;
+    uint32_t rows = 0;
+    const uint32_t bands = (h + band_rows - 1) / band_rows;
+    for (uint32_t b = rank; b < bands; b += n_ranks) {
+        const uint32_t begin = b * band_rows;
+        const uint32_t end = begin + band_rows < h ? begin + band_rows : h;
+        rows += end - begin;
+    }
+    return rows;
+}
+
+static int realloc_pipeline_buffers(bh_ray_pipeline *p)
+{
+    const size_t px = (size_t)p->local_rows * p->w;
+    if (p->own_out_rows != p->local_rows) {
+        if (p->own_out) cudaFree(p->own_out);
+        if (p->queue) cudaFree(p->queue);
+        p->own_out = nullptr; p->queue = nullptr;
+        BH_CUDA(cudaMalloc(&p->own_out, (px ? px : 1) * sizeof(float4)));
+        BH_CUDA(cudaMalloc(&p->queue, (px ? px : 1) * sizeof(unsigned)));
+        p->own_out_rows = p->local_rows;
+        if (p->aux_hit) { cudaFree(p->aux_hit); p->aux_hit = nullptr; }
+        if (p->aux_steps) { cudaFree(p->aux_steps); p->aux_steps = nullptr; }
+        if (p->aux_class) { cudaFree(p->aux_class); p->aux_class = nullptr; }
+    }
+    if ((p->aux_mask & BH_AUX_HIT) && !p->aux_hit) BH_CUDA(cudaMalloc(&p->aux_hit, (px ? px : 1) * sizeof(int32_t)));
+    if ((p->aux_mask & BH_AUX_STEPS) && !p->aux_steps) BH_CUDA(cudaMalloc(&p->aux_steps, (px ? px : 1) * sizeof(uint32_t)));
+    if ((p->aux_mask & BH_AUX_CLASS) && !p->aux_class) BH_CUDA(cudaMalloc(&p->aux_class, (px ? px : 1) * sizeof(uint8_t)));
+    return BH_OK;
+}
+
+extern "C" {
+
+int bh_abi_version(void) { return BH_ABI_VERSION; }
+const char *bh_last_error(void) { return g_error; }
+
+// ------------------------------------------------------------------------------------------ context
+int bh_ctx_create(int cuda_device, bh_ctx **out)
+{
+    if (!out) { set_error("bh_ctx_create: out is NULL"); return BH_ERR_INVALID; }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        set_error("bh_ctx_create: no CUDA device (%s); this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        cudaGetLastError();
+        return BH_ERR_NODEV;
+    }
+    if (cuda_device < 0 || cuda_device >= n) { set_error("bh_ctx_create: device %d out of range [0,%d)", cuda_device, n); return BH_ERR_INVALID; }
+    BH_CUDA(cudaSetDevice(cuda_device));
+    cudaDeviceProp prop;
+    BH_CUDA(cudaGetDeviceProperties(&prop, cuda_device));
+    if (prop.major != 10) {
+        set_error("bh_ctx_create: device %d is sm_%d%d; libbhray is built for sm_100a (B200) only", cuda_device, prop.major, prop.minor);
+        return BH_ERR_NODEV;
+    }
+    bh_ctx *c = new (std::nothrow) bh_ctx();
+    if (!c) { set_error("bh_ctx_create: out of host memory"); return BH_ERR_NOMEM; }
+    c->device = cuda_device;
+    c->sm_count = prop.multiProcessorCount;
+    *out = c;
+    return BH_OK;
+}
+
+void bh_ctx_destroy(bh_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (auto &t : ctx->tex) if (t) cudaFree(t);
+    if (ctx->models) cudaFree(ctx->models);
+    delete ctx;
+}
+
+int bh_ctx_set_texture(bh_ctx *ctx, bh_texture_slot slot, const uint8_t *rgba8, uint32_t w, uint32_t h)
+{
+    if (!ctx || !rgba8 || (int)slot < 0 || (int)slot > 2 || w == 0 || h == 0 || w > 32768 || h > 32768) {
+        set_error("bh_ctx_set_texture: bad argument (slot=%d, %ux%u)", (int)slot, w, h);
+        return BH_ERR_INVALID;
+    }
+    BH_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->tex[slot]) { cudaFree(ctx->tex[slot]); ctx->tex[slot] = nullptr; }
+    BH_CUDA(cudaMalloc(&ctx->tex[slot], (size_t)w * h * 4));
+    BH_CUDA(cudaMemcpy(ctx->tex[slot], rgba8, (size_t)w * h * 4, cudaMemcpyHostToDevice));
+    ctx->tex_w[slot] = (int)w; ctx->tex_h[slot] = (int)h;
+    return BH_OK;
+}
+
+static int upload_models(bh_ctx *ctx, const void *bytes, size_t nbytes, bool async, cudaStream_t stream)
+{
+    if (!ctx || (!bytes && nbytes) || nbytes % BH_MODEL_UNIFORM_SIZE != 0 || nbytes / BH_MODEL_UNIFORM_SIZE > BH_MAX_MODELS) {
+        set_error("bh_ctx_upload_models: nbytes=%zu is not count*%d with count <= %d", nbytes, BH_MODEL_UNIFORM_SIZE, BH_MAX_MODELS);
+        return BH_ERR_INVALID;
+    }
+    BH_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->models) BH_CUDA(cudaMalloc(&ctx->models, (size_t)BH_MAX_MODELS * kModelStride));
+    const int count = (int)(nbytes / BH_MODEL_UNIFORM_SIZE);
+    for (int i = 0; i < count; ++i) {
+        const unsigned char *src = static_cast<const unsigned char *>(bytes) + (size_t)i * BH_MODEL_UNIFORM_SIZE;
+        if (async) BH_CUDA(cudaMemcpyAsync(ctx->models + (size_t)i * kModelStride, src, BH_MODEL_UNIFORM_SIZE, cudaMemcpyHostToDevice, stream));
+        else BH_CUDA(cudaMemcpy(ctx->models + (size_t)i * kModelStride, src, BH_MODEL_UNIFORM_SIZE, cudaMemcpyHostToDevice));
+    }
+    ctx->models_uploaded = count;
+    return BH_OK;
+}
+
+int bh_ctx_upload_models(bh_ctx *ctx, const void *bytes, size_t nbytes) { return upload_models(ctx, bytes, nbytes, false, nullptr); }
+int bh_ctx_upload_models_async(bh_ctx *ctx, const void *pinned_bytes, size_t nbytes, void *cuda_stream)
+{
+    return upload_models(ctx, pinned_bytes, nbytes, true, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int bh_ctx_set_model_header(bh_ctx *ctx, uint32_t index, const float position[3], int32_t visible)
+{
+    if (!ctx || !position || (int)index >= ctx->models_uploaded) { set_error("bh_ctx_set_model_header: bad argument"); return BH_ERR_INVALID; }
+    BH_CUDA(cudaSetDevice(ctx->device));
+    unsigned char hdr[16];
+    memcpy(hdr, position, 12);
+    memcpy(hdr + 12, &visible, 4);
+    BH_CUDA(cudaMemcpy(ctx->models + (size_t)index * kModelStride, hdr, 16, cudaMemcpyHostToDevice));
+    return BH_OK;
+}
+
+// ------------------------------------------------------------------------------------------ ray pass
+int bh_ray_pipeline_create(bh_ctx *ctx, uint32_t width, uint32_t height, const bh_ray_pipeline *prev, bh_ray_pipeline **out)
+{
+    if (!out) { set_error("bh_ray_pipeline_create: out is NULL"); return BH_ERR_INVALID; }
+    *out = nullptr;
+    if (!ctx || width < 2 || height < 2 || width > 65535 || height > 65535) {
+        set_error("bh_ray_pipeline_create: resolution %ux%u out of range [2,65535]", width, height);
+        return BH_ERR_INVALID;
+    }
+    if (prev && (prev->ctx != ctx || prev->w < 2 || prev->h < 2)) { set_error("bh_ray_pipeline_create: prev belongs to another context"); return BH_ERR_INVALID; }
+    if (prev && prev->n_ranks != 1) { set_error("bh_ray_pipeline_create: prev level must be untiled (coarse levels are replicated)"); return BH_ERR_INVALID; }
+    BH_CUDA(cudaSetDevice(ctx->device));
+    bh_ray_pipeline *p = new (std::nothrow) bh_ray_pipeline();
+    if (!p) { set_error("bh_ray_pipeline_create: out of host memory"); return BH_ERR_NOMEM; }
+    p->ctx = ctx; p->w = width; p->h = height; p->prev = prev;
+    p->band_rows = height; p->rank = 0; p->n_ranks = 1; p->local_rows = height;
+    int rc = realloc_pipeline_buffers(p);
+    if (rc == BH_OK) {
+        cudaError_t e = cudaMalloc(&p->stats, sizeof(unsigned long long) * kStatCount);
+        if (e == cudaSuccess) e = cudaMalloc(&p->work, sizeof(unsigned) * kWorkCount);
+        if (e == cudaSuccess) e = cudaMemset(p->stats, 0, sizeof(unsigned long long) * kStatCount);
+        if (e != cudaSuccess) rc = cuda_fail(e, "bh_ray_pipeline_create: cudaMalloc");
+    }
+    if (rc != BH_OK) { bh_ray_pipeline_destroy(p); return rc; }
+    *out = p;
+    return BH_OK;
+}
+
+void bh_ray_pipeline_destroy(bh_ray_pipeline *p)
+{
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    if (p->ran) cudaStreamSynchronize(p->last_stream);
+    for (void *q : { (void *)p->own_out, (void *)p->aux_hit, (void *)p->aux_steps, (void *)p->aux_class, (void *)p->stats, (void *)p->work, (void *)p->queue })
+        if (q) cudaFree(q);
+    delete p;
+}
+
+int bh_ray_pipeline_set_tiling(bh_ray_pipeline *p, uint32_t band_rows, uint32_t rank, uint32_t n_ranks)
+{
+    if (!p || band_rows == 0 || n_ranks == 0 || rank >= n_ranks) { set_error("bh_ray_pipeline_set_tiling: bad argument"); return BH_ERR_INVALID; }
+    BH_CUDA(cudaSetDevice(p->ctx->device));
+    if (p->ran) BH_CUDA(cudaStreamSynchronize(p->last_stream));
+    p->band_rows = band_rows; p->rank = rank; p->n_ranks = n_ranks;
+    p->local_rows = count_local_rows(p->h, band_rows, rank, n_ranks);
+    return realloc_pipeline_buffers(p);
+}
+
+uint32_t bh_ray_pipeline_local_rows(const bh_ray_pipeline *p) { return p ? p->local_rows : 0; }
+uint32_t bh_ray_pipeline_width(const bh_ray_pipeline *p) { return p ? p->w : 0; }
+uint32_t bh_ray_pipeline_height(const bh_ray_pipeline *p) { return p ? p->h : 0; }
+
+int bh_ray_pipeline_enable_aux(bh_ray_pipeline *p, uint32_t aux_mask)
+{
+    if (!p || (aux_mask & ~7u)) { set_error("bh_ray_pipeline_enable_aux: bad argument"); return BH_ERR_INVALID; }
+    BH_CUDA(cudaSetDevice(p->ctx->device));
+    if (p->ran) BH_CUDA(cudaStreamSynchronize(p->last_stream));
+    p->aux_mask = aux_mask;
+    if (!(aux_mask & BH_AUX_HIT) && p->aux_hit) { cudaFree(p->aux_hit); p->aux_hit = nullptr; }
+    if (!(aux_mask & BH_AUX_STEPS) && p->aux_steps) { cudaFree(p->aux_steps); p->aux_steps = nullptr; }
+    if (!(aux_mask & BH_AUX_CLASS) && p->aux_class) { cudaFree(p->aux_class); p->aux_class = nullptr; }
+    return realloc_pipeline_buffers(p);
+}
+
+int bh_ray_pipeline_bind_output(bh_ray_pipeline *p, void *device_rgba32f)
+{
+    if (!p || ((uintptr_t)device_rgba32f & 15u)) { set_error("bh_ray_pipeline_bind_output: pointer must be 16-byte aligned"); return BH_ERR_INVALID; }
+    p->bound_out = static_cast<float4 *>(device_rgba32f);
+    return BH_OK;
+}
+
+int bh_ray_pipeline_pass(bh_ray_pipeline *p, const bh_camera_uniform *camera, const bh_black_hole_uniform *black_hole,
+                         const bh_ray_details *details, void *cuda_stream)
+{
+    if (!p || !camera || !black_hole || !details) { set_error("bh_ray_pipeline_pass: NULL argument"); return BH_ERR_INVALID; }
+    bh_ctx *c = p->ctx;
+    if (!c->tex[0] || !c->tex[1] || !c->tex[2]) { set_error("bh_ray_pipeline_pass: textures not set (bh_ctx_set_texture for COLOR, DISK and SKY)"); return BH_ERR_STATE; }
+    if (details->model_count < 0 || details->model_count > c->models_uploaded) {
+        set_error("bh_ray_pipeline_pass: model_count=%d but %d model(s) uploaded", details->model_count, c->models_uploaded);
+        return BH_ERR_INVALID;
+    }
+    if (details->integration_method != 0 && details->integration_method != 1) {
+        // ray.wgsl:525: anything non-zero takes the RK branch
+    }
+    BH_CUDA(cudaSetDevice(c->device));
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    PassParams P;
+    memset(&P, 0, sizeof P);
+    P.cam = *camera; P.hole = *black_hole; P.det = *details;
+    if (P.det.integration_method != 0) P.det.integration_method = 1;
+    P.color = DevTexture{ c->tex[0], c->tex_w[0], c->tex_h[0] };
+    P.disk = DevTexture{ c->tex[1], c->tex_w[1], c->tex_h[1] };
+    P.sky = DevTexture{ c->tex[2], c->tex_w[2], c->tex_h[2] };
+    P.models = c->models;
+    P.out = p->out();
+    P.prev = p->prev ? p->prev->out() : nullptr;
+    P.w = (int)p->w; P.h = (int)p->h;
+    P.pw = p->prev ? (int)p->prev->w : 1; P.ph = p->prev ? (int)p->prev->h : 1;
+    P.band_rows = (int)p->band_rows; P.rank = (int)p->rank; P.n_ranks = (int)p->n_ranks; P.local_rows = (int)p->local_rows;
+    P.aux_hit = p->aux_hit; P.aux_steps = p->aux_steps; P.aux_class = p->aux_class;
+    P.stats = p->stats; P.work = p->work; P.queue = p->queue;
+    P.tiles_x = (int)((p->w + 7) / 8);
+    P.n_items = (unsigned)P.tiles_x * (unsigned)((p->local_rows + 3) / 4);
+    LaunchConfig cfg{ c->sm_count };
+    p->last_stream = stream; p->ran = true;
+    if (p->local_rows == 0) return BH_OK;
+    BH_CUDA(launch_ray_pass(P, cfg, stream));
+    return BH_OK;
+}
+
+const float *bh_ray_pipeline_output(const bh_ray_pipeline *p) { return p ? reinterpret_cast<const float *>(p->out()) : nullptr; }
+
+int bh_ray_pipeline_read(bh_ray_pipeline *p, float *host_rgba32f, int32_t *host_hit, uint32_t *host_steps, uint8_t *host_class)
+{
+    if (!p) { set_error("bh_ray_pipeline_read: NULL pipeline"); return BH_ERR_INVALID; }
+    if (!p->ran) { set_error("bh_ray_pipeline_read: no pass has been enqueued"); return BH_ERR_STATE; }
+    if ((host_hit && !p->aux_hit) || (host_steps && !p->aux_steps) || (host_class && !p->aux_class)) {
+        set_error("bh_ray_pipeline_read: aux buffer requested but not enabled (bh_ray_pipeline_enable_aux)");
+        return BH_ERR_STATE;
+    }
+    BH_CUDA(cudaSetDevice(p->ctx->device));
+    BH_CUDA(cudaStreamSynchronize(p->last_stream));
+    const size_t px = (size_t)p->local_rows * p->w;
+    if (host_rgba32f) BH_CUDA(cudaMemcpy(host_rgba32f, p->out(), px * sizeof(float4), cudaMemcpyDeviceToHost));
+    if (host_hit) BH_CUDA(cudaMemcpy(host_hit, p->aux_hit, px * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (host_steps) BH_CUDA(cudaMemcpy(host_steps, p->aux_steps, px * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (host_class) BH_CUDA(cudaMemcpy(host_class, p->aux_class, px * sizeof(uint8_t), cudaMemcpyDeviceToHost));
+    return BH_OK;
+}
+
+int bh_ray_pipeline_stats(bh_ray_pipeline *p, bh_pass_stats *out)
+{
+    if (!p || !out) { set_error("bh_ray_pipeline_stats: NULL argument"); return BH_ERR_INVALID; }
+    if (!p->ran) { set_error("bh_ray_pipeline_stats: no pass has been enqueued"); return BH_ERR_STATE; }
+    BH_CUDA(cudaSetDevice(p->ctx->device));
+    BH_CUDA(cudaStreamSynchronize(p->last_stream));
+    unsigned long long s[kStatCount];
+    BH_CUDA(cudaMemcpy(s, p->stats, sizeof s, cudaMemcpyDeviceToHost));
+    out->ray_steps = s[kStatSteps]; out->px_traced = s[kStatTraced]; out->px_copied = s[kStatCopied]; out->px_interp = s[kStatInterp];
+    out->node_visits = s[kStatNodeVisits]; out->tri_tests = s[kStatTriTests]; out->tex_samples = s[kStatTexSamples];
+    out->rk_reject = s[kStatRkReject]; out->stack_overflow = s[kStatStackOverflow];
+    if (out->rk_reject) {
+        set_error("bh_ray_pipeline_stats: %llu ray(s) had an RK error norm > 1; the reference's accept loop (ray.wgsl:425-451) would not terminate",
+                  (unsigned long long)out->rk_reject);
+        return BH_ERR_NUMERIC;
+    }
+    return BH_OK;
+}
+
+// ------------------------------------------------------------------------------------------ sky pass
+int bh_sky_pipeline_create(bh_ctx *ctx, const bh_ray_pipeline *prev, bh_sky_format format, bh_sky_pipeline **out)
+{
+    if (!out) { set_error("bh_sky_pipeline_create: out is NULL"); return BH_ERR_INVALID; }
+    *out = nullptr;
+    if (!ctx || !prev || prev->ctx != ctx || ((int)format != 0 && (int)format != 1)) { set_error("bh_sky_pipeline_create: bad argument"); return BH_ERR_INVALID; }
+    BH_CUDA(cudaSetDevice(ctx->device));
+    bh_sky_pipeline *s = new (std::nothrow) bh_sky_pipeline();
+    if (!s) { set_error("bh_sky_pipeline_create: out of host memory"); return BH_ERR_NOMEM; }
+    s->ctx = ctx; s->prev = prev; s->format = format;
+    // sized for the whole frame so that a later set_tiling on prev cannot outgrow it
+    cudaError_t e = cudaMalloc(&s->own_out, (size_t)prev->w * prev->h * s->texel_bytes());
+    if (e == cudaSuccess) e = cudaMalloc(&s->stats, sizeof(unsigned long long) * kStatCount);
+    if (e == cudaSuccess) e = cudaMemset(s->stats, 0, sizeof(unsigned long long) * kStatCount);
+    if (e != cudaSuccess) { const int rc = cuda_fail(e, "bh_sky_pipeline_create: cudaMalloc"); bh_sky_pipeline_destroy(s); return rc; }
+    *out = s;
+    return BH_OK;
+}
+
+void bh_sky_pipeline_destroy(bh_sky_pipeline *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    if (s->ran) cudaStreamSynchronize(s->last_stream);
+    if (s->own_out) cudaFree(s->own_out);
+    if (s->stats) cudaFree(s->stats);
+    delete s;
+}
+
+int bh_sky_pipeline_bind_output(bh_sky_pipeline *s, void *device_rgba)
+{
+    if (!s || ((uintptr_t)device_rgba & 15u)) { set_error("bh_sky_pipeline_bind_output: pointer must be 16-byte aligned"); return BH_ERR_INVALID; }
+    s->bound_out = device_rgba;
+    return BH_OK;
+}
+
+int bh_sky_pipeline_pass(bh_sky_pipeline *s, void *cuda_stream)
+{
+    if (!s) { set_error("bh_sky_pipeline_pass: NULL pipeline"); return BH_ERR_INVALID; }
+    bh_ctx *c = s->ctx;
+    if (!c->tex[2]) { set_error("bh_sky_pipeline_pass: sky texture not set"); return BH_ERR_STATE; }
+    BH_CUDA(cudaSetDevice(c->device));
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    SkyParams S;
+    memset(&S, 0, sizeof S);
+    S.sky = DevTexture{ c->tex[2], c->tex_w[2], c->tex_h[2] };
+    S.prev = s->prev->out();
+    S.out = s->out();
+    S.n_pixels = (int)((size_t)s->prev->local_rows * s->prev->w);
+    S.format = (int)s->format;
+    S.stats = s->stats;
+    s->last_stream = stream; s->ran = true;
+    if (S.n_pixels == 0) return BH_OK;
+    BH_CUDA(cudaMemsetAsync(s->stats, 0, sizeof(unsigned long long) * kStatCount, stream));
+    LaunchConfig cfg{ c->sm_count };
+    BH_CUDA(launch_sky_pass(S, cfg, stream));
+    return BH_OK;
+}
+
+const void *bh_sky_pipeline_output(const bh_sky_pipeline *s) { return s ? s->out() : nullptr; }
+
+int bh_sky_pipeline_read(bh_sky_pipeline *s, void *host_rgba)
+{
+    if (!s || !host_rgba) { set_error("bh_sky_pipeline_read: NULL argument"); return BH_ERR_INVALID; }
+    if (!s->ran) { set_error("bh_sky_pipeline_read: no pass has been enqueued"); return BH_ERR_STATE; }
+    BH_CUDA(cudaSetDevice(s->ctx->device));
+    BH_CUDA(cudaStreamSynchronize(s->last_stream));
+    BH_CUDA(cudaMemcpy(host_rgba, s->out(), (size_t)s->prev->local_rows * s->prev->w * s->texel_bytes(), cudaMemcpyDeviceToHost));
+    return BH_OK;
+}
+
+// ------------------------------------------------------------------------------------------ math probe
+int bh_ctx_math_probe(bh_ctx *ctx, int fn, const float *host_a, const float *host_b, float *host_out, size_t n)
+{
+    if (!ctx || !host_a || !host_out || fn < 0 || fn > 7) { set_error("bh_ctx_math_probe: bad argument"); return BH_ERR_INVALID; }
+    if (n == 0) return BH_OK;
+    BH_CUDA(cudaSetDevice(ctx->device));
+    float *a = nullptr, *b = nullptr, *o = nullptr;
+    cudaError_t e = cudaMalloc(&a, n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&b, n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&o, n * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(a, host_a, n * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = host_b ? cudaMemcpy(b, host_b, n * 4, cudaMemcpyHostToDevice) : cudaMemset(b, 0, n * 4);
+    if (e == cudaSuccess) e = launch_math_probe(fn, a, b, o, n, nullptr);
+    if (e == cudaSuccess) e = cudaMemcpy(host_out, o, n * 4, cudaMemcpyDeviceToHost);
+    if (a) cudaFree(a);
+    if (b) cudaFree(b);
+    if (o) cudaFree(o);
+    if (e != cudaSuccess) return cuda_fail(e, "bh_ctx_math_probe");
+    return BH_OK;
+}
+
+}  // extern "C"

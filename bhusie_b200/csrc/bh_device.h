@@ -1,0 +1,73 @@
+// bh_device.h — structures shared by the C-ABI host code (bh_abi.cu) and the kernels (ray_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/bh_abi.h"
+
+namespace bh {
+
+// RGBA8 unorm texture in linear device memory (texture.rs:32: Rgba8Unorm; filtering is done in
+// fp32 in the kernel — CUDA's hardware filter has 9-bit weights).
+struct DevTexture {
+    const uchar4 *texels;
+    int w, h;
+};
+
+// ModelUniform byte offsets (src/renderer/triangle.rs:268-285)
+constexpr size_t kMuPosition  = 0;
+constexpr size_t kMuVisible   = 12;
+constexpr size_t kMuPoints    = 48;
+constexpr size_t kMuNormals   = 8388656;
+constexpr size_t kMuTriangles = 16777264;
+constexpr size_t kMuNodes     = 29360176;
+constexpr size_t kMuLookup    = 46137392;
+// device copies of consecutive models are placed at a 256-byte-aligned stride so that the
+// 16-byte vector loads of nodes/points stay aligned for every model index
+constexpr size_t kModelStride = (BH_MODEL_UNIFORM_SIZE + 255) / 256 * 256;
+
+enum StatIndex : int {
+    kStatSteps = 0, kStatTraced, kStatCopied, kStatInterp, kStatNodeVisits, kStatTriTests,
+    kStatTexSamples, kStatRkReject, kStatStackOverflow, kStatCount
+};
+
+enum WorkIndex : int { kWorkNext = 0, kWorkQueueLen = 1, kWorkCount = 4 };
+
+struct PassParams {
+    bh_camera_uniform cam;
+    bh_black_hole_uniform hole;
+    bh_ray_details det;
+    DevTexture color, disk, sky;
+    const unsigned char *models;     // kModelStride per model
+    float4 *out;                     // local_rows x w
+    const float4 *prev;              // ph x pw (nullptr: base level)
+    int w, h, pw, ph;
+    int band_rows, rank, n_ranks, local_rows;
+    int32_t *aux_hit;                // nullable
+    uint32_t *aux_steps;             // nullable
+    uint8_t *aux_class;              // nullable
+    unsigned long long *stats;       // kStatCount
+    unsigned int *work;              // kWorkCount
+    unsigned int *queue;             // local pixel indices awaiting a trace (fine levels)
+    unsigned int n_items;            // tile mode: number of 8x4 warp tiles
+    int tiles_x;
+};
+
+struct SkyParams {
+    DevTexture sky;
+    const float4 *prev;
+    void *out;
+    int n_pixels;
+    int format;                      // bh_sky_format
+    unsigned long long *stats;
+};
+
+struct LaunchConfig {
+    int sm_count;
+};
+
+// launchers (ray_kernels.cu)
+cudaError_t launch_ray_pass(const PassParams &p, const LaunchConfig &cfg, cudaStream_t stream);
+cudaError_t launch_sky_pass(const SkyParams &p, const LaunchConfig &cfg, cudaStream_t stream);
+cudaError_t launch_math_probe(int fn, const float *a, const float *b, float *out, size_t n, cudaStream_t stream);
+
+}  // namespace bh

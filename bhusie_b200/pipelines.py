@@ -1,0 +1,267 @@
+"""Host-side mirror of the reference's pass objects for the ray path, on top of the C ABI.
+
+    reference (Rust, wgpu)                                   here
+    -------------------------------------------------------  ----------------------------------
+    Device/Queue + Renderer-owned scene buffers (mod.rs:63-114)  Context
+    RayPipeline::new / output_view / pass  (ray_pipeline.rs)     RayPipeline(...) / .output_ptr / .pass()
+    SkyPipeline::new / output_view / pass  (sky_pipeline.rs)     SkyPipeline(...) / .output_ptr / .pass()
+    4-level pyramid + sky in one compute pass (mod.rs:170-216,406-421)  RayPyramid
+
+`pass_()` only enqueues on a CUDA stream, like recording into a ComputePass; `read()` synchronises.
+All computation happens in libbhray.so; nothing here falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .uniforms import (BLACK_HOLE_UNIFORM_SIZE, CAMERA_UNIFORM_SIZE, MODEL_UNIFORM_SIZE, RAY_DETAILS_SIZE,
+                       BlackHole, Camera, RayDetails, pyramid_levels)
+
+TEX_COLOR, TEX_DISK, TEX_SKY = 0, 1, 2
+AUX_HIT, AUX_STEPS, AUX_CLASS = 1, 2, 4
+SKY_RGBA16F, SKY_RGBA32F = 0, 1
+
+
+def _bytes(x, size: int) -> bytes:
+    b = x.uniform() if hasattr(x, "uniform") else bytes(x)
+    if len(b) != size:
+        raise ValueError(f"uniform must be {size} bytes, got {len(b)}")
+    return b
+
+
+def _stream_ptr(stream) -> C.c_void_p:
+    if stream is None:
+        return C.c_void_p(0)
+    if hasattr(stream, "cuda_stream"):          # torch.cuda.Stream
+        return C.c_void_p(stream.cuda_stream)
+    return C.c_void_p(int(stream))
+
+
+class Context:
+    """Owns the device copies of the scene: three textures and the ModelUniform array."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self._lib.bh_ctx_create(device, C.byref(h)))
+        self._h = h
+        self.device = device
+        self.model_count = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.bh_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_texture(self, slot: int, rgba8: np.ndarray):
+        a = np.ascontiguousarray(rgba8, dtype=np.uint8)
+        if a.ndim != 3 or a.shape[2] != 4:
+            raise ValueError("texture must be (h, w, 4) uint8")
+        _lib.check(self._lib.bh_ctx_set_texture(self._h, slot, a.ctypes.data_as(C.c_void_p), a.shape[1], a.shape[0]))
+
+    def set_textures(self, tex: dict):
+        self.set_texture(TEX_COLOR, tex["color"])
+        self.set_texture(TEX_DISK, tex["disk"])
+        self.set_texture(TEX_SKY, tex["sky"])
+
+    def upload_models(self, blob: np.ndarray | None):
+        if blob is None:
+            self.model_count = 0
+            return
+        a = np.ascontiguousarray(blob, dtype=np.uint8).reshape(-1)
+        _lib.check(self._lib.bh_ctx_upload_models(self._h, a.ctypes.data_as(C.c_void_p), a.size))
+        self.model_count = a.size // MODEL_UNIFORM_SIZE
+
+    def upload_models_async(self, host_ptr: int, nbytes: int, stream=None):
+        _lib.check(self._lib.bh_ctx_upload_models_async(self._h, C.c_void_p(host_ptr), nbytes, _stream_ptr(stream)))
+        self.model_count = nbytes // MODEL_UNIFORM_SIZE
+
+    def set_model_header(self, index: int, position, visible: int):
+        pos = (C.c_float * 3)(*map(float, position))
+        _lib.check(self._lib.bh_ctx_set_model_header(self._h, index, pos, int(visible)))
+
+    def math_probe(self, fn: str, a: np.ndarray, b: np.ndarray | None = None) -> np.ndarray:
+        codes = {"pow": 0, "pow5": 1, "pow4": 2, "sin": 3, "cos": 4, "tan": 5, "atan2": 6, "acos": 7}
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        bb = None if b is None else np.ascontiguousarray(b, dtype=np.float32)
+        out = np.empty_like(a)
+        _lib.check(self._lib.bh_ctx_math_probe(self._h, codes[fn], a.ctypes.data_as(C.c_void_p),
+                                               None if bb is None else bb.ctypes.data_as(C.c_void_p),
+                                               out.ctypes.data_as(C.c_void_p), a.size))
+        return out
+
+
+class RayPipeline:
+    """RayPipeline::new (ray_pipeline.rs:36): `prev=None` is the 1x1 base texture (mod.rs:151-168)."""
+
+    def __init__(self, ctx: Context, width: int, height: int, prev: "RayPipeline | None" = None, aux: int = 0):
+        self._lib = ctx._lib
+        self.ctx = ctx
+        self.prev = prev
+        self.width, self.height = int(width), int(height)
+        h = C.c_void_p()
+        _lib.check(self._lib.bh_ray_pipeline_create(ctx._h, self.width, self.height, prev._h if prev else None, C.byref(h)))
+        self._h = h
+        self._aux = 0
+        if aux:
+            self.enable_aux(aux)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.bh_ray_pipeline_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def enable_aux(self, mask: int):
+        _lib.check(self._lib.bh_ray_pipeline_enable_aux(self._h, mask))
+        self._aux = mask
+
+    def set_tiling(self, band_rows: int, rank: int, n_ranks: int):
+        _lib.check(self._lib.bh_ray_pipeline_set_tiling(self._h, band_rows, rank, n_ranks))
+
+    @property
+    def local_rows(self) -> int:
+        return int(self._lib.bh_ray_pipeline_local_rows(self._h))
+
+    def bind_output(self, device_ptr: int | None):
+        _lib.check(self._lib.bh_ray_pipeline_bind_output(self._h, C.c_void_p(device_ptr or 0)))
+
+    @property
+    def output_ptr(self) -> int:
+        """RayPipeline::output_view: device pointer to row-major RGBA32F."""
+        return int(self._lib.bh_ray_pipeline_output(self._h) or 0)
+
+    def pass_(self, camera, black_hole, details, stream=None):
+        """RayPipeline::pass (ray_pipeline.rs:301-309): enqueue on `stream`, return immediately."""
+        cam = _bytes(camera, CAMERA_UNIFORM_SIZE)
+        hole = _bytes(black_hole, BLACK_HOLE_UNIFORM_SIZE)
+        det = _bytes(details, RAY_DETAILS_SIZE)
+        _lib.check(self._lib.bh_ray_pipeline_pass(self._h, cam, hole, det, _stream_ptr(stream)))
+
+    def read(self, aux: bool = True) -> dict:
+        rows, w = self.local_rows, self.width
+        out = {"rgba": np.empty((rows, w, 4), np.float32)}
+        hit = steps = cls = None
+        if aux and self._aux & AUX_HIT:
+            hit = out["hit"] = np.empty((rows, w), np.int32)
+        if aux and self._aux & AUX_STEPS:
+            steps = out["steps"] = np.empty((rows, w), np.uint32)
+        if aux and self._aux & AUX_CLASS:
+            cls = out["cls"] = np.empty((rows, w), np.uint8)
+        p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        _lib.check(self._lib.bh_ray_pipeline_read(self._h, p(out["rgba"]), p(hit), p(steps), p(cls)))
+        return out
+
+    def read_into(self, host_ptr: int):
+        _lib.check(self._lib.bh_ray_pipeline_read(self._h, C.c_void_p(host_ptr), None, None, None))
+
+    def stats(self) -> dict:
+        s = _lib.PassStats()
+        _lib.check(self._lib.bh_ray_pipeline_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+
+class SkyPipeline:
+    """SkyPipeline::new (sky_pipeline.rs:18): resolves alpha==0 pixels of `prev` against the sky map."""
+
+    def __init__(self, ctx: Context, prev: RayPipeline, fmt: int = SKY_RGBA16F):
+        self._lib = ctx._lib
+        self.ctx, self.prev, self.fmt = ctx, prev, fmt
+        h = C.c_void_p()
+        _lib.check(self._lib.bh_sky_pipeline_create(ctx._h, prev._h, fmt, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.bh_sky_pipeline_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def bind_output(self, device_ptr: int | None):
+        _lib.check(self._lib.bh_sky_pipeline_bind_output(self._h, C.c_void_p(device_ptr or 0)))
+
+    @property
+    def output_ptr(self) -> int:
+        return int(self._lib.bh_sky_pipeline_output(self._h) or 0)
+
+    def pass_(self, stream=None):
+        _lib.check(self._lib.bh_sky_pipeline_pass(self._h, _stream_ptr(stream)))
+
+    def read(self) -> np.ndarray:
+        rows, w = self.prev.local_rows, self.prev.width
+        out = np.empty((rows, w, 4), np.float32 if self.fmt == SKY_RGBA32F else np.float16)
+        _lib.check(self._lib.bh_sky_pipeline_read(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+
+class RayPyramid:
+    """The reference's adaptive grid: `iters` RayPipelines, level n reading level n-1, then the sky
+    resolve — what Renderer::new builds (mod.rs:170-216) and Renderer::render dispatches in one
+    compute pass (mod.rs:406-421)."""
+
+    def __init__(self, ctx: Context, base=(72, 41), multiplier: int = 3, iters: int = 4, aux: int = 0,
+                 sky_format: int = SKY_RGBA16F):
+        self.ctx = ctx
+        self.sizes = pyramid_levels(base, multiplier, iters)
+        self.levels: list[RayPipeline] = []
+        for (w, h) in self.sizes:
+            self.levels.append(RayPipeline(ctx, w, h, self.levels[-1] if self.levels else None, aux=aux))
+        self.sky = SkyPipeline(ctx, self.levels[-1], sky_format)
+
+    def pass_(self, camera, black_hole, details, stream=None):
+        for rp in self.levels:
+            rp.pass_(camera, black_hole, details, stream)
+        self.sky.pass_(stream)
+
+    def close(self):
+        self.sky.close()
+        for rp in reversed(self.levels):
+            rp.close()
+
+
+def load_obj_model(path: str) -> tuple[np.ndarray, dict]:
+    """load_model (model.rs:7-87) + build_bvh through the library's host code -> ModelUniform bytes."""
+    lib = _lib.load()
+    blob = np.zeros(MODEL_UNIFORM_SIZE, np.uint8)
+    info = _lib.ModelInfo()
+    _lib.check(lib.bh_model_load_obj(path.encode(), blob.ctypes.data_as(C.c_void_p), C.byref(info)))
+    return blob, info.as_dict()
+
+
+def model_from_arrays(points: np.ndarray, normals: np.ndarray, tris: np.ndarray, position=(-10.0, 0.0, 30.0),
+                      visible: int = 1) -> tuple[np.ndarray, dict]:
+    lib = _lib.load()
+    pts = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+    nrm = np.ascontiguousarray(normals, np.float32).reshape(-1, 3)
+    tr = np.ascontiguousarray(tris, np.int32).reshape(-1, 6)
+    blob = np.zeros(MODEL_UNIFORM_SIZE, np.uint8)
+    info = _lib.ModelInfo()
+    pos = (C.c_float * 3)(*map(float, position))
+    _lib.check(lib.bh_model_from_arrays(pts.ctypes.data_as(C.c_void_p), len(pts), nrm.ctypes.data_as(C.c_void_p), len(nrm),
+                                        tr.ctypes.data_as(C.c_void_p), len(tr), pos, int(visible),
+                                        blob.ctypes.data_as(C.c_void_p), C.byref(info)))
+    return blob, info.as_dict()
+
+
+__all__ = ["Context", "RayPipeline", "SkyPipeline", "RayPyramid", "Camera", "BlackHole", "RayDetails",
+           "load_obj_model", "model_from_arrays", "TEX_COLOR", "TEX_DISK", "TEX_SKY", "AUX_HIT", "AUX_STEPS",
+           "AUX_CLASS", "SKY_RGBA16F", "SKY_RGBA32F"]

@@ -1,0 +1,196 @@
+/* bh_abi.h — C ABI of libbhray.so: bhusie's per-pixel geodesic ray pass on B200 (sm_100a).
+ *
+ * The reference has no FFI surface; its boundary for this path is the Rust pass-object API in
+ * src/renderer/pipelines/ (paths below are relative to the cleggacus/bhusie tree):
+ *
+ *   RayPipelineDescriptor{device,queue,resolution,camera_buffer,black_hole_buffer,material_buffer,
+ *                         model_buffer,ray_details_buffer,prev_texture_view}   ray_pipeline.rs:16-26
+ *   RayPipeline::new(descriptor) -> Self                                       ray_pipeline.rs:36-295
+ *   RayPipeline::output_view(&self) -> &TextureView                            ray_pipeline.rs:297-299
+ *   RayPipeline::pass(&mut self, &mut ComputePass)                             ray_pipeline.rs:301-309
+ *   SkyPipeline::{new, output_view, pass}                                      sky_pipeline.rs:18,136,140
+ *
+ * Each entry point below names the reference item it replaces.  Conventions: every function
+ * returns 0 on success or a negative errno-style code (never throws or aborts across the
+ * boundary); bh_last_error() gives the text for the calling thread.  The caller owns all host
+ * memory; the library owns all device memory unless bh_*_bind_output is used.  One context per
+ * CUDA device; calls on one context are not re-entrant (the reference drives its passes from one
+ * thread, src/app.rs:108-114); different contexts may be driven from different threads.
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails with BH_ERR_NODEV.
+ *
+ * The three small uniforms cross the ABI as the verbatim bytes of the reference's #[repr(C)]
+ * structs (what it passes to queue.write_buffer at src/renderer/mod.rs:386-388).
+ */
+#ifndef BH_ABI_H
+#define BH_ABI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BH_ABI_VERSION 1
+
+/* error codes (negative errno values) */
+#define BH_OK            0
+#define BH_ERR_INVALID  (-22)   /* EINVAL: bad argument */
+#define BH_ERR_NOMEM    (-12)   /* ENOMEM: host or device allocation failed */
+#define BH_ERR_NODEV    (-19)   /* ENODEV: no usable CUDA device */
+#define BH_ERR_CUDA     (-5)    /* EIO:    a CUDA call failed (text in bh_last_error) */
+#define BH_ERR_STATE    (-1)    /* EPERM:  call sequence error (e.g. pass before textures are set) */
+#define BH_ERR_NOENT    (-2)    /* ENOENT: file not found */
+#define BH_ERR_TOOBIG   (-7)    /* E2BIG:  mesh exceeds MAX_MODEL_VERTICES */
+#define BH_ERR_NUMERIC  (-34)   /* ERANGE: the RK accept loop of ray.wgsl:425-451 would not terminate (e_max > 1) */
+
+/* ---- uniform byte layouts (verbatim) ------------------------------------ */
+
+typedef struct bh_camera_uniform {          /* CameraUniform, src/scene/camera.rs:66-73 */
+    float position[3]; uint32_t _padding;
+    float forward[3];  float fov;
+} bh_camera_uniform;                        /* 32 B */
+
+typedef struct bh_black_hole_uniform {      /* BlackHoleUniform, src/scene/blackhole.rs:37-51 */
+    float accretion_disk_inner, accretion_disk_outer, rotation_speed, relativity_sphere_radius;
+    float position[3]; int32_t show_disk_texture;
+    float normal[3];   int32_t show_red_shift;
+    float rotation_matrix[12];              /* three columns (right, up, forward), each vec3 + pad */
+    float feather_amount;
+    int32_t pad[8];
+} bh_black_hole_uniform;                    /* 132 B */
+
+typedef struct bh_ray_details {             /* RayDetails, src/renderer/pipelines/ray_pipeline.rs:3-14 */
+    int32_t material_count, model_count;
+    float   time;
+    int32_t integration_method;             /* 0 Euler, 1 Cash–Karp RK (ray.wgsl:29) */
+    float   step_size;
+    int32_t max_iterations;
+    float   angle_division_threshold;
+    int32_t highlight_interpolation;
+} bh_ray_details;                           /* 32 B */
+
+#define BH_MAX_MODEL_VERTICES 524288        /* src/renderer/triangle.rs:7 */
+#define BH_MAX_MODELS         1             /* src/renderer/triangle.rs:6 */
+#define BH_MODEL_UNIFORM_SIZE 48234572      /* sizeof(ModelUniform), src/renderer/triangle.rs:268-285 */
+
+typedef enum bh_texture_slot {              /* the three include_bytes! textures, ray_pipeline.rs:63-70 */
+    BH_TEX_COLOR = 0,                       /* color.png  256x256   (t_temp, ray.wgsl:13)  */
+    BH_TEX_DISK  = 1,                       /* disk.png   1000x1000 (t_disk, ray.wgsl:15)  */
+    BH_TEX_SKY   = 2                        /* sky.png    6000x3000 (t_sky,  ray.wgsl:17)  */
+} bh_texture_slot;
+
+typedef struct bh_ctx          bh_ctx;
+typedef struct bh_ray_pipeline bh_ray_pipeline;
+typedef struct bh_sky_pipeline bh_sky_pipeline;
+
+/* ---- library ------------------------------------------------------------------------------- */
+int         bh_abi_version(void);
+const char *bh_last_error(void);            /* thread-local text of the last failure ("" if none) */
+
+/* ---- context: replaces the wgpu Device/Queue pair + Renderer-owned scene buffers
+ *      (src/renderer/mod.rs:63-89,113-114) ---------------------------------------------------- */
+int  bh_ctx_create(int cuda_device, bh_ctx **out);
+void bh_ctx_destroy(bh_ctx *ctx);
+
+/* texture::Texture::from_bytes (src/renderer/texture.rs:10-80) minus the PNG decode: RGBA8 unorm
+ * (no sRGB), bilinear, clamp-to-edge, one mip.  Copies rgba8 (w*h*4 bytes) to the device. */
+int  bh_ctx_set_texture(bh_ctx *ctx, bh_texture_slot slot, const uint8_t *rgba8, uint32_t w, uint32_t h);
+
+/* ModelArrayBuffer::update_buffer (src/renderer/array_buffer.rs:71-79): `bytes` is
+ * ModelUniform[count] verbatim, nbytes == count*BH_MODEL_UNIFORM_SIZE, count <= BH_MAX_MODELS.
+ * Synchronous (returns after the copy).  bh_ctx_upload_models_async enqueues the same copy on
+ * `cuda_stream` from caller-pinned memory (the reference re-sends the blob every frame). */
+int  bh_ctx_upload_models(bh_ctx *ctx, const void *bytes, size_t nbytes);
+int  bh_ctx_upload_models_async(bh_ctx *ctx, const void *pinned_bytes, size_t nbytes, void *cuda_stream);
+/* cheap per-frame update of ModelUniform.position/.visible (the fields the UI edits,
+ * src/ui/model_settings.rs:39-48) without re-sending 48 MB */
+int  bh_ctx_set_model_header(bh_ctx *ctx, uint32_t index, const float position[3], int32_t visible);
+
+/* ---- ray pass: replaces RayPipeline -------------------------------------------------------- */
+/* RayPipeline::new.  prev == NULL is the 1x1 "base" texture of mod.rs:151-168 (every pixel traced);
+ * otherwise prev's output is this level's t_prev (ray.wgsl:19) and must outlive this object. */
+int  bh_ray_pipeline_create(bh_ctx *ctx, uint32_t width, uint32_t height,
+                            const bh_ray_pipeline *prev, bh_ray_pipeline **out);
+void bh_ray_pipeline_destroy(bh_ray_pipeline *p);
+
+/* Image-space sharding for multi-GPU (no reference counterpart): this pipeline renders
+ * only the cyclic row bands  { y : (y / band_rows) % n_ranks == rank }  of the width x height frame
+ * into a compact band-major buffer of bh_ray_pipeline_local_rows() rows.  Default (1 rank): whole frame. */
+int      bh_ray_pipeline_set_tiling(bh_ray_pipeline *p, uint32_t band_rows, uint32_t rank, uint32_t n_ranks);
+uint32_t bh_ray_pipeline_local_rows(const bh_ray_pipeline *p);
+
+/* Optional per-pixel aux buffers for validation: bit 0 = BVH hit triangle index (int32, value of
+ * `index` at ray.wgsl:333 for the composited triangle, -1 if none), bit 1 = integrator step count
+ * (uint32), bit 2 = pixel class (uint8: 0 traced/base 1 copied 2 interpolated 3 traced/fine). */
+#define BH_AUX_HIT   1u
+#define BH_AUX_STEPS 2u
+#define BH_AUX_CLASS 4u
+int  bh_ray_pipeline_enable_aux(bh_ray_pipeline *p, uint32_t aux_mask);
+
+/* Render into caller-owned device memory (local_rows*width*16 B, 16-byte aligned) instead of the
+ * pipeline's own buffer — lets the host hand in a torch tensor / NCCL send buffer.  NULL restores. */
+int  bh_ray_pipeline_bind_output(bh_ray_pipeline *p, void *device_rgba32f);
+
+/* RayPipeline::pass: enqueue the pass on `cuda_stream` (a cudaStream_t; NULL = default stream) and
+ * return — same contract as recording into a ComputePass.  The three pointers are HOST bytes, read
+ * before return. */
+int  bh_ray_pipeline_pass(bh_ray_pipeline *p, const bh_camera_uniform *camera,
+                          const bh_black_hole_uniform *black_hole, const bh_ray_details *details,
+                          void *cuda_stream);
+
+/* RayPipeline::output_view: device pointer, row-major RGBA32F, pitch = width*16 B, local_rows rows.
+ * alpha==1: finished colour; alpha==0: rgb is the escaped-ray direction (ray.wgsl:592-595). */
+const float *bh_ray_pipeline_output(const bh_ray_pipeline *p);
+uint32_t     bh_ray_pipeline_width(const bh_ray_pipeline *p);
+uint32_t     bh_ray_pipeline_height(const bh_ray_pipeline *p);
+
+/* Synchronous read-back (waits for the last pass).  Every pointer is nullable. */
+int  bh_ray_pipeline_read(bh_ray_pipeline *p, float *host_rgba32f, int32_t *host_hit,
+                          uint32_t *host_steps, uint8_t *host_class);
+
+typedef struct bh_pass_stats {              /* totals of the last pass (waits for it) */
+    uint64_t ray_steps;                     /* integrator calls: next_ray_rk / next_ray_euler (ray.wgsl:525-531) */
+    uint64_t px_traced, px_copied, px_interp;
+    uint64_t node_visits, tri_tests;        /* BVH inner-node visits / hit_triangle calls */
+    uint64_t tex_samples;                   /* bilinear samples taken (disk, LUT, sky) */
+    uint64_t rk_reject;                     /* rays whose RK error norm exceeded 1 (reference would spin; Q5) */
+    uint64_t stack_overflow;                /* BVH pushes beyond the reference's 19-entry stack (Q16) */
+} bh_pass_stats;
+int  bh_ray_pipeline_stats(bh_ray_pipeline *p, bh_pass_stats *out);
+
+/* ---- sky resolve: replaces SkyPipeline ----------------------------------------------------- */
+typedef enum bh_sky_format {
+    BH_SKY_RGBA16F = 0,                     /* the reference's Rgba16Float (sky_pipeline.rs:34) */
+    BH_SKY_RGBA32F = 1                      /* the value before the f16 store (parity) */
+} bh_sky_format;
+int  bh_sky_pipeline_create(bh_ctx *ctx, const bh_ray_pipeline *prev, bh_sky_format format, bh_sky_pipeline **out);
+void bh_sky_pipeline_destroy(bh_sky_pipeline *p);
+int  bh_sky_pipeline_bind_output(bh_sky_pipeline *p, void *device_rgba);
+int  bh_sky_pipeline_pass(bh_sky_pipeline *p, void *cuda_stream);
+const void *bh_sky_pipeline_output(const bh_sky_pipeline *p);
+int  bh_sky_pipeline_read(bh_sky_pipeline *p, void *host_rgba);   /* local_rows*width*(8|16) B */
+
+/* ---- host-side scene preparation: replaces load_model + Model::build_bvh ---------------------
+ * (src/renderer/model.rs:7-87, src/renderer/triangle.rs:143-259).  Pure host code; `model_uniform`
+ * is a caller-owned BH_MODEL_UNIFORM_SIZE-byte buffer that receives the verbatim ModelUniform. */
+typedef struct bh_model_info {
+    int32_t point_count, normal_count, triangle_count;
+    int32_t nodes_used, max_depth, leaf_count, max_leaf_size;
+} bh_model_info;
+int  bh_model_load_obj(const char *path, void *model_uniform, bh_model_info *info);
+/* points/normals: n*3 floats already in model space; tris: m*6 int32 (p1,p2,p3,n1,n2,n3) */
+int  bh_model_from_arrays(const float *points, int32_t n_points, const float *normals, int32_t n_normals,
+                          const int32_t *tris, int32_t n_tris, const float position[3], int32_t visible,
+                          void *model_uniform, bh_model_info *info);
+int  bh_model_build_bvh(void *model_uniform, int32_t triangle_count, bh_model_info *info);
+
+/* ---- device math probe (tests only): evaluates the kernel's det-math on the device so that
+ *      tests can compare it bit-for-bit with the oracle's contract flavour.
+ *      fn: 0 pow(a,b) 1 pow5(a) 2 pow4(a) 3 sin 4 cos 5 tan 6 atan2(a,b) 7 acos ------------------ */
+int  bh_ctx_math_probe(bh_ctx *ctx, int fn, const float *host_a, const float *host_b, float *host_out, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BH_ABI_H */
