@@ -1,0 +1,372 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle.
+
+Gates:
+  * vs the oracle's CONTRACT flavour: bit-exact RGBA32F, hit-triangle indices, step counts, classes;
+  * vs the oracle's STRICT flavour (glibc libm): |diff| <= 1e-4 per channel (north-star tolerance) on
+    all but a stated tiny fraction of pixels, hit indices and step counts equal on >= 99.9 %;
+  * at BASELINE.json's full sizes: size-independent properties + oracle spot-checks on sampled rows.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import bits
+from bhusie_b200 import _lib, assets, pipelines as P, uniforms as U
+from bhusie_b200.multi import BandLayout
+
+pytestmark = pytest.mark.gpu
+
+AUX = P.AUX_HIT | P.AUX_STEPS | P.AUX_CLASS
+TOL = 1e-4                 # BASELINE.json north_star: 1e-4 per RGBA channel
+STRICT_OUTLIER_FRAC = 2e-3  # pixels allowed beyond TOL vs the libm flavour (chaotic rays near the photon sphere / star edges)
+
+
+@pytest.fixture(scope="module")
+def ctx_small(small_scene):
+    tex, blob, _ = small_scene
+    ctx = P.Context(0)
+    ctx.set_textures(tex)
+    ctx.upload_models(blob)
+    yield ctx
+    ctx.close()
+
+
+@pytest.fixture(scope="module")
+def real_scene(oracle):
+    tex, src = assets.load_textures()
+    if assets.have_lucy():
+        blob, info = P.load_obj_model(assets.lucy_path())
+    else:
+        blob, info = P.model_from_arrays(*assets.uv_sphere())
+    ctx = P.Context(0)
+    ctx.set_textures(tex)
+    ctx.upload_models(blob)
+    osc = oracle.OracleScene(tex["color"], tex["disk"], tex["sky"], blob)
+    yield ctx, osc, src
+    ctx.close()
+
+
+def render(ctx, w, h, cam, hole, det, prev=None, aux=AUX):
+    rp = P.RayPipeline(ctx, w, h, prev, aux=aux)
+    rp.pass_(cam, hole, det)
+    return rp, rp.read(), rp.stats()
+
+
+def assert_bit_exact(dev, ora, what=""):
+    assert np.array_equal(bits(dev["rgba"]), bits(ora.rgba)), f"{what}: RGBA not bit-exact ({(bits(dev['rgba']) != bits(ora.rgba)).mean():.3%} words differ)"
+    assert np.array_equal(dev["hit"], ora.hit), f"{what}: hit indices differ"
+    assert np.array_equal(dev["steps"], ora.steps), f"{what}: step counts differ"
+    assert np.array_equal(dev["cls"], ora.cls), f"{what}: classes differ"
+
+
+def assert_stats(st, counters):
+    assert st["ray_steps"] == counters["steps"]
+    assert st["px_traced"] == counters["px_traced"] and st["px_copied"] == counters["px_copied"] and st["px_interp"] == counters["px_interp"]
+    assert st["node_visits"] == counters["node_visits"] and st["tri_tests"] == counters["tri_tests"]
+    assert st["tex_samples"] == counters["tex_samples"]
+    assert st["rk_reject"] == 0 and st["stack_overflow"] == counters["stack_overflow"]
+
+
+def assert_close_to_strict(dev, strict, what=""):
+    d = np.abs(dev["rgba"].astype(np.float64) - strict.rgba.astype(np.float64))
+    bad = (d > TOL).any(axis=2).mean()
+    assert bad <= STRICT_OUTLIER_FRAC, f"{what}: {bad:.4%} of pixels beyond {TOL} vs libm oracle (max {d.max():.3g})"
+    assert (dev["hit"] == strict.hit).mean() >= 0.999 and (dev["steps"] == strict.steps).mean() >= 0.999
+
+
+# ------------------------------------------------------------------ det-math: device == oracle contract flavour, bit for bit
+def test_detmath_bit_exact(ctx_small, oracle):
+    rng = np.random.default_rng(21)
+    n = 400000
+    sp = np.float32([0, -0.0, 1, -1, np.inf, -np.inf, np.nan, 1e-45, 3.4e38, 1e-38, 2, 0.5])
+    cases = {
+        "pow": (np.concatenate([rng.uniform(0, 60, n), sp, sp]), np.concatenate([rng.uniform(-5, 5, n), sp, sp[::-1]])),
+        "pow5": (np.concatenate([rng.uniform(0, 200, n), sp]), None), "pow4": (np.concatenate([rng.uniform(0, 1, n), sp]), None),
+        "sin": (np.concatenate([rng.uniform(-1e4, 1e4, n), sp]), None), "cos": (np.concatenate([rng.uniform(-1e4, 1e4, n), sp]), None),
+        "tan": (np.concatenate([rng.uniform(-3, 3, n), sp]), None),
+        "atan2": (np.concatenate([rng.normal(size=n), sp, sp]), np.concatenate([rng.normal(size=n), sp, sp[::-1]])),
+        "acos": (np.concatenate([rng.uniform(-1.001, 1.001, n), sp]), None),
+    }
+    for fn, (a, b) in cases.items():
+        a = a.astype(np.float32)
+        b = None if b is None else b.astype(np.float32)
+        dev = ctx_small.math_probe(fn, a, b)
+        ora = oracle.math_array(fn, a, b, flavour="contract")
+        same = (bits(dev) == bits(ora)) | (np.isnan(dev) & np.isnan(ora))
+        assert same.all(), (fn, a[~same][:5], None if b is None else b[~same][:5], dev[~same][:5], ora[~same][:5])
+
+
+# ------------------------------------------------------------------ single-level passes, small scene
+@pytest.mark.parametrize("method", [0, 1])
+@pytest.mark.parametrize("campos,fwd", [((0, 0, -19), (0, 0, 1)), ((0, 0, -45), (0, 0, 1)), ((-28, 4, 24), (0.6, -0.1, 0.2)), ((3, 1, -6), (0, 0, 1))])
+def test_small_scene_bit_exact(ctx_small, oracle, small_oracle_scene, method, campos, fwd):
+    cam, hole = U.Camera(position=campos, forward=fwd), U.BlackHole()
+    det = U.RayDetails(integration_method=method, model_count=1, time=1.25)
+    w, h = 96, 54
+    rp, dev, st = render(ctx_small, w, h, cam, hole, det)
+    ora = oracle.ray_pass(small_oracle_scene, w, h, cam.uniform(), hole.uniform(), det.uniform(), flavour="contract")
+    assert_bit_exact(dev, ora, f"method {method} cam {campos}")
+    assert_stats(st, ora.counters)
+    strict = oracle.ray_pass(small_oracle_scene, w, h, cam.uniform(), hole.uniform(), det.uniform(), flavour="strict")
+    assert_close_to_strict(dev, strict)
+    rp.close()
+
+
+@pytest.mark.parametrize("variant", ["no_texture", "no_shift", "neither", "moved_hole", "wide_disk", "big_step", "short", "feather0", "invisible", "nomodel"])
+def test_parameter_variants_bit_exact(ctx_small, oracle, small_oracle_scene, variant):
+    hole, det, cam = U.BlackHole(), U.RayDetails(integration_method=1, model_count=1), U.Camera()
+    if variant == "no_texture": hole.show_disk_texture = 0
+    if variant == "no_shift": hole.show_red_shift = 0
+    if variant == "neither": hole.show_disk_texture = hole.show_red_shift = 0
+    if variant == "moved_hole": hole.position = (1.5, -0.5, 2.0)
+    if variant == "wide_disk": hole.accretion_disk_inner, hole.accretion_disk_outer, hole.accretion_disk_rotation = 3.0, 16.0, (1.2, 0.3, -0.4)
+    if variant == "big_step": det.step_size = 0.8
+    if variant == "short": det.max_iterations = 40
+    if variant == "feather0": hole.feather_amount = 1.0
+    if variant == "nomodel": det.model_count = 0
+    if variant == "invisible":
+        ctx_small.set_model_header(0, (-10.0, 0.0, 30.0), 0)
+    try:
+        w, h = 80, 45
+        rp, dev, st = render(ctx_small, w, h, cam, hole, det)
+        osc = small_oracle_scene
+        if variant == "invisible":
+            blob = osc.models.copy()
+            blob[12:16].view(np.int32)[0] = 0
+            osc = oracle.OracleScene(osc.color, osc.disk, osc.sky, blob)
+        ora = oracle.ray_pass(osc, w, h, cam.uniform(), hole.uniform(), det.uniform(), flavour="contract")
+        assert_bit_exact(dev, ora, variant)
+        assert_stats(st, ora.counters)
+        if variant in ("invisible", "nomodel"):
+            assert np.all(dev["hit"] == -1) and st["tri_tests"] == 0
+        rp.close()
+    finally:
+        if variant == "invisible":
+            ctx_small.set_model_header(0, (-10.0, 0.0, 30.0), 1)
+
+
+def test_ragged_sizes_bit_exact(ctx_small, oracle, small_oracle_scene):
+    """Frame sizes that are not multiples of the 8x4 warp tile, down to the 2x2 minimum."""
+    cam, hole, det = U.Camera(), U.BlackHole(), U.RayDetails(integration_method=1, model_count=1)
+    for (w, h) in ((2, 2), (9, 5), (33, 7), (7, 33), (65, 37)):
+        rp, dev, st = render(ctx_small, w, h, cam, hole, det)
+        ora = oracle.ray_pass(small_oracle_scene, w, h, cam.uniform(), hole.uniform(), det.uniform(), flavour="contract")
+        assert_bit_exact(dev, ora, f"{w}x{h}")
+        assert_stats(st, ora.counters)
+        rp.close()
+
+
+# ------------------------------------------------------------------ adaptive grid + sky resolve
+@pytest.mark.parametrize("thr", [0.02, 0.08])
+def test_pyramid_and_sky_bit_exact(ctx_small, oracle, small_oracle_scene, thr):
+    cam, hole = U.Camera(), U.BlackHole()
+    det = U.RayDetails(integration_method=1, model_count=1, angle_division_threshold=thr)
+    pyr = P.RayPyramid(ctx_small, base=(32, 18), iters=3, aux=AUX, sky_format=P.SKY_RGBA32F)
+    assert pyr.sizes == [(32, 18), (94, 52), (280, 154)]
+    pyr.pass_(cam, hole, det)
+    prev = None
+    for rp in pyr.levels:
+        dev = rp.read()
+        ora = oracle.ray_pass(small_oracle_scene, rp.width, rp.height, cam.uniform(), hole.uniform(), det.uniform(), prev=prev, flavour="contract")
+        assert_bit_exact(dev, ora, f"level {rp.width}x{rp.height}")
+        assert_stats(rp.stats(), ora.counters)
+        prev = ora.rgba
+    if thr == 0.08:
+        assert pyr.levels[2].stats()["px_interp"] > 10000
+    sky32 = pyr.sky.read()
+    o32, o16, cnt = oracle.sky_pass(small_oracle_scene, prev, flavour="contract")
+    assert np.array_equal(bits(sky32), bits(o32))
+    assert np.all(sky32[..., 3] == 1)
+    sky16 = P.SkyPipeline(ctx_small, pyr.levels[-1], P.SKY_RGBA16F)       # the reference's Rgba16Float target
+    sky16.pass_()
+    assert np.array_equal(sky16.read().view(np.uint16), o16)
+    sky16.close()
+    pyr.close()
+
+
+# ------------------------------------------------------------------ reference assets: C1, mesh cameras, reference pyramid geometry
+def test_c1_config(real_scene, oracle):
+    """BASELINE.json configs[0]: 256x256 single frame, Euler, disk only, no meshes."""
+    ctx, osc, src = real_scene
+    cam, hole, det = U.Camera(), U.BlackHole(), U.RayDetails(integration_method=0, model_count=0)
+    rp, dev, st = render(ctx, 256, 256, cam, hole, det)
+    ora = oracle.ray_pass(osc, 256, 256, cam.uniform(), hole.uniform(), det.uniform(), flavour="contract")
+    assert_bit_exact(dev, ora, "C1")
+    assert_stats(st, ora.counters)
+    assert_close_to_strict(dev, oracle.ray_pass(osc, 256, 256, cam.uniform(), hole.uniform(), det.uniform(), flavour="strict"), "C1")
+    rp.close()
+
+
+@pytest.mark.parametrize("campos,fwd", [((0, 0, -19), (0, 0, 1)), ((0, 0, -45), (0, 0, 1)), ((-30, 5, 30), (0.6, -0.1, 0.0))])
+def test_mesh_scene_hit_indices(real_scene, oracle, campos, fwd):
+    """BVH hit indices bit-exact (north star) on the 100k-triangle mesh, camera inside and outside R_rel."""
+    ctx, osc, src = real_scene
+    cam, hole, det = U.Camera(position=campos, forward=fwd), U.BlackHole(), U.RayDetails(integration_method=1, model_count=1)
+    w, h = 384, 216
+    rp, dev, st = render(ctx, w, h, cam, hole, det)
+    ora = oracle.ray_pass(osc, w, h, cam.uniform(), hole.uniform(), det.uniform(), flavour="contract")
+    assert_bit_exact(dev, ora, f"mesh cam {campos}")
+    assert_stats(st, ora.counters)
+    assert (dev["hit"] >= 0).sum() > 500
+    assert st["stack_overflow"] == 0          # Q16: the 19-entry stack never overflows in the test configs
+    strict = oracle.ray_pass(osc, w, h, cam.uniform(), hole.uniform(), det.uniform(), flavour="strict")
+    assert_close_to_strict(dev, strict, f"mesh cam {campos}")
+    rp.close()
+
+
+def test_reference_pyramid_first_levels(real_scene, oracle):
+    """The reference's own level sizes 72x41 -> 214x121 -> 640x361 (mod.rs:177-206), default threshold."""
+    ctx, osc, src = real_scene
+    cam, hole, det = U.Camera(), U.BlackHole(), U.RayDetails(integration_method=1, model_count=1)
+    pyr = P.RayPyramid(ctx, iters=3, aux=AUX, sky_format=P.SKY_RGBA16F)
+    assert pyr.sizes == [(72, 41), (214, 121), (640, 361)]
+    pyr.pass_(cam, hole, det)
+    prev = None
+    for rp in pyr.levels:
+        dev = rp.read()
+        ora = oracle.ray_pass(osc, rp.width, rp.height, cam.uniform(), hole.uniform(), det.uniform(), prev=prev, flavour="contract")
+        assert_bit_exact(dev, ora, f"level {rp.width}x{rp.height}")
+        prev = ora.rgba
+    assert pyr.levels[2].stats()["px_interp"] > 50000
+    _, o16, _ = oracle.sky_pass(osc, prev, flavour="contract")
+    assert np.array_equal(pyr.sky.read().view(np.uint16), o16)
+    pyr.close()
+
+
+# ------------------------------------------------------------------ tiling (multi-GPU sharding) on one device
+@pytest.mark.parametrize("band,world", [(8, 2), (4, 3), (5, 8), (16, 4)])
+def test_tiled_bands_equal_full_frame(ctx_small, band, world):
+    cam, hole, det = U.Camera(), U.BlackHole(), U.RayDetails(integration_method=1, model_count=1)
+    w, h = 120, 67
+    rp, full, _ = render(ctx_small, w, h, cam, hole, det)
+    lay = BandLayout(h, band, world)
+    steps_total = 0
+    for rank in range(world):
+        t = P.RayPipeline(ctx_small, w, h, aux=AUX)
+        t.set_tiling(band, rank, world)
+        assert t.local_rows == lay.local_rows(rank)
+        t.pass_(cam, hole, det)
+        part = t.read()
+        rows = lay.rows_of(rank)
+        assert np.array_equal(bits(part["rgba"]), bits(full["rgba"][rows]))
+        assert np.array_equal(part["hit"], full["hit"][rows]) and np.array_equal(part["steps"], full["steps"][rows])
+        steps_total += t.stats()["ray_steps"]
+        t.close()
+    assert steps_total == int(full["steps"].sum())
+    rp.close()
+
+
+def test_tiled_pyramid_level(ctx_small, oracle, small_oracle_scene):
+    """A tiled fine level reading an untiled (replicated) coarse level."""
+    cam, hole = U.Camera(), U.BlackHole()
+    det = U.RayDetails(integration_method=1, model_count=1, angle_division_threshold=0.08)
+    l0 = P.RayPipeline(ctx_small, 32, 18)
+    l0.pass_(cam, hole, det)
+    prev = l0.read()["rgba"]
+    ora = oracle.ray_pass(small_oracle_scene, 94, 52, cam.uniform(), hole.uniform(), det.uniform(), prev=prev, flavour="contract")
+    lay = BandLayout(52, 4, 3)
+    for rank in range(3):
+        t = P.RayPipeline(ctx_small, 94, 52, l0, aux=AUX)
+        t.set_tiling(4, rank, 3)
+        t.pass_(cam, hole, det)
+        part = t.read()
+        rows = lay.rows_of(rank)
+        assert np.array_equal(bits(part["rgba"]), bits(ora.rgba[rows])) and np.array_equal(part["cls"], ora.cls[rows])
+        t.close()
+    l0.close()
+
+
+# ------------------------------------------------------------------ API behaviour
+def test_bind_output_and_streams(ctx_small):
+    import torch
+    cam, hole, det = U.Camera(), U.BlackHole(), U.RayDetails(integration_method=1, model_count=1)
+    w, h = 64, 36
+    rp, own, _ = render(ctx_small, w, h, cam, hole, det, aux=0)
+    buf = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+    s = torch.cuda.Stream()
+    rp.bind_output(buf.data_ptr())
+    assert rp.output_ptr == buf.data_ptr()
+    with torch.cuda.stream(s):
+        rp.pass_(cam, hole, det, s)
+    s.synchronize()
+    assert np.array_equal(bits(buf.cpu().numpy()), bits(own["rgba"]))
+    rp.bind_output(None)
+    rp.pass_(cam, hole, det)                                        # idempotent: same bits again
+    assert np.array_equal(bits(rp.read()["rgba"]), bits(own["rgba"]))
+    rp.close()
+
+
+def test_error_codes(small_scene):
+    tex, blob, _ = small_scene
+    lib = _lib.load()
+    ctx = P.Context(0)
+    rp = P.RayPipeline(ctx, 16, 9)
+    with pytest.raises(_lib.BhError) as e:
+        rp.pass_(U.Camera(), U.BlackHole(), U.RayDetails())          # textures not set
+    assert e.value.code == -1
+    ctx.set_textures(tex)
+    with pytest.raises(_lib.BhError) as e:
+        rp.pass_(U.Camera(), U.BlackHole(), U.RayDetails(model_count=1))   # no model uploaded
+    assert e.value.code == -22
+    with pytest.raises(_lib.BhError):
+        rp.read()                                                     # nothing enqueued yet
+    with pytest.raises(_lib.BhError):
+        P.RayPipeline(ctx, 1, 9)
+    with pytest.raises(_lib.BhError):
+        ctx.upload_models(np.zeros(100, np.uint8))
+    with pytest.raises(_lib.BhError):
+        rp.set_tiling(0, 0, 1)
+    with pytest.raises(_lib.BhError):
+        P.Context(99)
+    with pytest.raises(ValueError):
+        rp.pass_(b"short", U.BlackHole(), U.RayDetails())
+    rp.pass_(U.Camera(), U.BlackHole(), U.RayDetails())
+    host = np.zeros((9, 16), np.int32)
+    assert lib.bh_ray_pipeline_read(rp._h, None, host.ctypes.data_as(C.c_void_p), None, None) == -1    # aux not enabled
+    assert b"aux" in lib.bh_last_error()
+    rp.close()
+    ctx.close()
+
+
+# ------------------------------------------------------------------ BASELINE.json full sizes: properties + oracle spot checks
+@pytest.mark.parametrize("w,h,mc", [(1920, 1080, 0), (3840, 2160, 1)])
+def test_full_size_properties(real_scene, oracle, w, h, mc):
+    """C2 (1920x1080 RK, disk) and C3 (3840x2160 RK, disk + sphere + 100k-tri BVH): the oracle is too slow
+    for whole frames here, so check (a) oracle parity on sampled rows, (b) determinism, (c) step-count
+    bookkeeping, (d) output invariants."""
+    ctx, osc, src = real_scene
+    cam, hole, det = U.Camera(), U.BlackHole(), U.RayDetails(integration_method=1, model_count=mc)
+    rp, dev, st = render(ctx, w, h, cam, hole, det, aux=P.AUX_HIT | P.AUX_STEPS)
+    rows = sorted({0, h // 7, h // 3, h // 2 - 1, h // 2, (2 * h) // 3, h - 1})
+    for y in rows:                                                   # (a)
+        ora = oracle.ray_pass(osc, w, h, cam.uniform(), hole.uniform(), det.uniform(), rows=(y, y + 1), flavour="contract")
+        assert np.array_equal(bits(dev["rgba"][y]), bits(ora.rgba[y])), f"row {y}"
+        assert np.array_equal(dev["hit"][y], ora.hit[y]) and np.array_equal(dev["steps"][y], ora.steps[y])
+    assert st["ray_steps"] == int(dev["steps"].sum(dtype=np.int64))  # (c)
+    assert st["px_traced"] == w * h and st["rk_reject"] == 0 and st["stack_overflow"] == 0
+    a = dev["rgba"][..., 3]
+    assert np.all((a == 0) | (a == 1))                               # (d) alpha is a flag
+    esc = a == 0
+    n = np.linalg.norm(dev["rgba"][..., :3][esc].astype(np.float64), axis=1)
+    assert np.all(np.abs(n - 1) < 0.2) and np.isfinite(dev["rgba"]).all()   # escaped directions (feather blend is not renormalised, Q9)
+    assert np.all(dev["hit"][esc] == -1)
+    if mc:
+        assert (dev["hit"] >= 0).sum() > 10000
+    rp.pass_(cam, hole, det)                                         # (b)
+    again = rp.read()
+    assert np.array_equal(bits(again["rgba"]), bits(dev["rgba"])) and np.array_equal(again["steps"], dev["steps"])
+    rp.close()
+
+
+def test_step_sweep_property(real_scene):
+    """C5: with relativity_radius = 1000 every ray that does not hit anything runs exactly max_iterations steps."""
+    ctx, osc, src = real_scene
+    cam, hole = U.Camera(), U.BlackHole(relativity_sphere_radius=1000.0)
+    for mi in (64, 256):
+        det = U.RayDetails(integration_method=1, model_count=0, max_iterations=mi)
+        rp, dev, st = render(ctx, 480, 270, cam, hole, det, aux=P.AUX_STEPS)
+        assert dev["steps"].max() == mi
+        unfinished = dev["rgba"][..., 3] == 0
+        assert np.all(dev["steps"][unfinished] == mi)
+        rp.close()
