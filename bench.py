@@ -332,8 +332,9 @@ def main():
     ap.add_argument("--height", type=int, default=2160)
     ap.add_argument("--band-rows", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--allow-short-warmup", action="store_true", help="profiling runs only (ncu); numbers from such runs are not bench values")
     args = ap.parse_args()
-    if args.warmup < 3 and args.impl == "ours":
+    if args.warmup < 3 and args.impl == "ours" and not args.allow_short_warmup:
         args.warmup = 3
     sys.exit(run_reference(args) if args.impl == "reference" else run_ours(args))
 

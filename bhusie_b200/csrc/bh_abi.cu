@@ -354,7 +354,7 @@ int bh_ray_pipeline_stats(bh_ray_pipeline *p, bh_pass_stats *out)
     out->node_visits = s[kStatNodeVisits]; out->tri_tests = s[kStatTriTests]; out->tex_samples = s[kStatTexSamples];
     out->rk_reject = s[kStatRkReject]; out->stack_overflow = s[kStatStackOverflow];
     if (out->rk_reject) {
-        set_error("bh_ray_pipeline_stats: %llu ray(s) had an RK error norm > 1; the reference's accept loop (ray.wgsl:425-451) would not terminate",
+        set_error("bh_ray_pipeline_stats: %llu RK step(s) had an error norm > 1; the reference's accept loop (ray.wgsl:425-451) would not terminate there",
                   (unsigned long long)out->rk_reject);
         return BH_ERR_NUMERIC;
     }

@@ -475,7 +475,6 @@ __device__ __forceinline__ LaneOut trace_warp(const PassParams &P, bool traced, 
     V3 col = mk(0.f, 0.f, 0.f);
     float closest_r = ray_distance;
     bool hit = false, finished = !traced;
-    bool reject = false;
     int i = 0;
     int tri = -1;
     unsigned nsteps = 0;
@@ -491,7 +490,7 @@ __device__ __forceinline__ LaneOut trace_warp(const PassParams &P, bool traced, 
                     step_euler(bhp, cp, cd, step);
                 } else {
                     const float e_max = step_rk(bhp, rp, rd, rh);
-                    if (!(e_max <= 1.0f)) reject = true;
+                    if (!(e_max <= 1.0f)) stat_add(P.stats, kStatRkReject, 1ULL);   // Q5: rare; the reference would spin here
                     cp = rp; cd = rd; step = rh;
                 }
                 ++nsteps;
@@ -555,7 +554,6 @@ __device__ __forceinline__ LaneOut trace_warp(const PassParams &P, bool traced, 
         } else {
             o.rgba = make_float4(cd.x, cd.y, cd.z, 0.0f);
         }
-        if (reject) stat_add(P.stats, kStatRkReject, 1ULL);
     } else {
         o.rgba = make_float4(0.f, 0.f, 0.f, 0.f);
     }

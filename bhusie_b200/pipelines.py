@@ -169,9 +169,13 @@ class RayPipeline:
     def read_into(self, host_ptr: int):
         _lib.check(self._lib.bh_ray_pipeline_read(self._h, C.c_void_p(host_ptr), None, None, None))
 
-    def stats(self) -> dict:
+    def stats(self, strict: bool = True) -> dict:
+        """Totals of the last pass.  strict: raise if any RK step had an error norm > 1 (BH_ERR_NUMERIC) —
+        the reference's accept loop would never terminate there (ray.wgsl:425-451)."""
         s = _lib.PassStats()
-        _lib.check(self._lib.bh_ray_pipeline_stats(self._h, C.byref(s)))
+        rc = self._lib.bh_ray_pipeline_stats(self._h, C.byref(s))
+        if rc != 0 and (strict or rc != -34):
+            _lib.check(rc)
         return s.as_dict()
 
 

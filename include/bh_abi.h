@@ -154,9 +154,10 @@ typedef struct bh_pass_stats {              /* totals of the last pass (waits fo
     uint64_t px_traced, px_copied, px_interp;
     uint64_t node_visits, tri_tests;        /* BVH inner-node visits / hit_triangle calls */
     uint64_t tex_samples;                   /* bilinear samples taken (disk, LUT, sky) */
-    uint64_t rk_reject;                     /* rays whose RK error norm exceeded 1 (reference would spin; Q5) */
+    uint64_t rk_reject;                     /* RK steps whose error norm exceeded 1 (reference would spin; Q5) */
     uint64_t stack_overflow;                /* BVH pushes beyond the reference's 19-entry stack (Q16) */
 } bh_pass_stats;
+/* Fills *out; returns BH_ERR_NUMERIC (with *out still valid) when rk_reject != 0. */
 int  bh_ray_pipeline_stats(bh_ray_pipeline *p, bh_pass_stats *out);
 
 /* ---- sky resolve: replaces SkyPipeline ----------------------------------------------------- */

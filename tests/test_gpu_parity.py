@@ -50,7 +50,7 @@ def real_scene(oracle):
 def render(ctx, w, h, cam, hole, det, prev=None, aux=AUX):
     rp = P.RayPipeline(ctx, w, h, prev, aux=aux)
     rp.pass_(cam, hole, det)
-    return rp, rp.read(), rp.stats()
+    return rp, rp.read(), rp.stats(strict=False)
 
 
 def assert_bit_exact(dev, ora, what=""):
@@ -65,7 +65,7 @@ def assert_stats(st, counters):
     assert st["px_traced"] == counters["px_traced"] and st["px_copied"] == counters["px_copied"] and st["px_interp"] == counters["px_interp"]
     assert st["node_visits"] == counters["node_visits"] and st["tri_tests"] == counters["tri_tests"]
     assert st["tex_samples"] == counters["tex_samples"]
-    assert st["rk_reject"] == 0 and st["stack_overflow"] == counters["stack_overflow"]
+    assert st["rk_reject"] == counters["rk_reject"] and st["stack_overflow"] == counters["stack_overflow"]
 
 
 def assert_close_to_strict(dev, strict, what=""):
@@ -138,6 +138,15 @@ def test_parameter_variants_bit_exact(ctx_small, oracle, small_oracle_scene, var
         ora = oracle.ray_pass(osc, w, h, cam.uniform(), hole.uniform(), det.uniform(), flavour="contract")
         assert_bit_exact(dev, ora, variant)
         assert_stats(st, ora.counters)
+        if variant == "moved_hole":
+            # Q1/Q5: h^2 uses p, not p - bh, so an off-origin hole drives some rays to an RK error norm > 1 where the
+            # reference shader would hang; the library flags it instead of spinning
+            assert st["rk_reject"] > 0
+            with pytest.raises(_lib.BhError) as e:
+                rp.stats()
+            assert e.value.code == -34
+        else:
+            assert st["rk_reject"] == 0
         if variant in ("invisible", "nomodel"):
             assert np.all(dev["hit"] == -1) and st["tri_tests"] == 0
         rp.close()
