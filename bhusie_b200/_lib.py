@@ -38,6 +38,8 @@ SYMBOLS = {
     "bh_last_error": (C.c_char_p, []),
     "bh_ctx_create": (C.c_int, [C.c_int, C.POINTER(_VP)]),
     "bh_ctx_destroy": (None, [_VP]),
+    "bh_ctx_set_numeric_mode": (C.c_int, [_VP, C.c_int]),
+    "bh_ctx_get_numeric_mode": (C.c_int, [_VP]),
     "bh_ctx_set_texture": (C.c_int, [_VP, C.c_int, _VP, _U32, _U32]),
     "bh_ctx_upload_models": (C.c_int, [_VP, _VP, C.c_size_t]),
     "bh_ctx_upload_models_async": (C.c_int, [_VP, _VP, C.c_size_t, _VP]),

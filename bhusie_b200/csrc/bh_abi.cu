@@ -53,6 +53,7 @@ struct bh_ctx {
     int tex_w[3] = { 0, 0, 0 }, tex_h[3] = { 0, 0, 0 };
     unsigned char *models = nullptr;     // BH_MAX_MODELS * kModelStride
     int models_uploaded = 0;
+    int numeric_mode = BH_NUMERIC_FUSED;
 };
 
 struct bh_ray_pipeline {
@@ -162,6 +163,15 @@ void bh_ctx_destroy(bh_ctx *ctx)
     if (ctx->models) cudaFree(ctx->models);
     delete ctx;
 }
+
+int bh_ctx_set_numeric_mode(bh_ctx *ctx, bh_numeric_mode mode)
+{
+    if (!ctx || ((int)mode != BH_NUMERIC_LITERAL && (int)mode != BH_NUMERIC_FUSED)) { set_error("bh_ctx_set_numeric_mode: bad argument"); return BH_ERR_INVALID; }
+    ctx->numeric_mode = (int)mode;
+    return BH_OK;
+}
+
+int bh_ctx_get_numeric_mode(const bh_ctx *ctx) { return ctx ? ctx->numeric_mode : BH_ERR_INVALID; }
 
 int bh_ctx_set_texture(bh_ctx *ctx, bh_texture_slot slot, const uint8_t *rgba8, uint32_t w, uint32_t h)
 {
@@ -315,7 +325,7 @@ int bh_ray_pipeline_pass(bh_ray_pipeline *p, const bh_camera_uniform *camera, co
     P.stats = p->stats; P.work = p->work; P.queue = p->queue;
     P.tiles_x = (int)((p->w + 7) / 8);
     P.n_items = (unsigned)P.tiles_x * (unsigned)((p->local_rows + 3) / 4);
-    LaunchConfig cfg{ c->sm_count };
+    LaunchConfig cfg{ c->sm_count, c->numeric_mode };
     p->last_stream = stream; p->ran = true;
     if (p->local_rows == 0) return BH_OK;
     BH_CUDA(launch_ray_pass(P, cfg, stream));
@@ -415,7 +425,7 @@ int bh_sky_pipeline_pass(bh_sky_pipeline *s, void *cuda_stream)
     s->last_stream = stream; s->ran = true;
     if (S.n_pixels == 0) return BH_OK;
     BH_CUDA(cudaMemsetAsync(s->stats, 0, sizeof(unsigned long long) * kStatCount, stream));
-    LaunchConfig cfg{ c->sm_count };
+    LaunchConfig cfg{ c->sm_count, c->numeric_mode };
     BH_CUDA(launch_sky_pass(S, cfg, stream));
     return BH_OK;
 }

@@ -63,6 +63,7 @@ struct SkyParams {
 
 struct LaunchConfig {
     int sm_count;
+    int numeric_mode;                // bh_numeric_mode
 };
 
 // launchers (ray_kernels.cu)

@@ -23,6 +23,9 @@ from .uniforms import (BLACK_HOLE_UNIFORM_SIZE, CAMERA_UNIFORM_SIZE, MODEL_UNIFO
 TEX_COLOR, TEX_DISK, TEX_SKY = 0, 1, 2
 AUX_HIT, AUX_STEPS, AUX_CLASS = 1, 2, 4
 SKY_RGBA16F, SKY_RGBA32F = 0, 1
+NUMERIC_LITERAL, NUMERIC_FUSED = 0, 1
+# which oracle flavour each kernel numeric mode is bit-comparable with (tests only; the product never imports the oracle)
+ORACLE_FLAVOUR_OF_MODE = {NUMERIC_LITERAL: "contract", NUMERIC_FUSED: "fused"}
 
 
 def _bytes(x, size: int) -> bytes:
@@ -43,13 +46,15 @@ def _stream_ptr(stream) -> C.c_void_p:
 class Context:
     """Owns the device copies of the scene: three textures and the ModelUniform array."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, numeric_mode: int | None = None):
         self._lib = _lib.load()
         h = C.c_void_p()
         _lib.check(self._lib.bh_ctx_create(device, C.byref(h)))
         self._h = h
         self.device = device
         self.model_count = 0
+        if numeric_mode is not None:
+            self.set_numeric_mode(numeric_mode)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -61,6 +66,14 @@ class Context:
             self.close()
         except Exception:
             pass
+
+    def set_numeric_mode(self, mode: int):
+        """LITERAL (one IEEE op per WGSL node) or FUSED (fma contraction + reciprocal-multiply; default)."""
+        _lib.check(self._lib.bh_ctx_set_numeric_mode(self._h, int(mode)))
+
+    @property
+    def numeric_mode(self) -> int:
+        return int(self._lib.bh_ctx_get_numeric_mode(self._h))
 
     def set_texture(self, slot: int, rgba8: np.ndarray):
         a = np.ascontiguousarray(rgba8, dtype=np.uint8)
@@ -268,4 +281,4 @@ def model_from_arrays(points: np.ndarray, normals: np.ndarray, tris: np.ndarray,
 
 __all__ = ["Context", "RayPipeline", "SkyPipeline", "RayPyramid", "Camera", "BlackHole", "RayDetails",
            "load_obj_model", "model_from_arrays", "TEX_COLOR", "TEX_DISK", "TEX_SKY", "AUX_HIT", "AUX_STEPS",
-           "AUX_CLASS", "SKY_RGBA16F", "SKY_RGBA32F"]
+           "AUX_CLASS", "SKY_RGBA16F", "SKY_RGBA32F", "NUMERIC_LITERAL", "NUMERIC_FUSED", "ORACLE_FLAVOUR_OF_MODE"]

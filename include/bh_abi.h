@@ -93,6 +93,16 @@ const char *bh_last_error(void);            /* thread-local text of the last fai
 int  bh_ctx_create(int cuda_device, bh_ctx **out);
 void bh_ctx_destroy(bh_ctx *ctx);
 
+/* Numeric mode of every kernel launched through this context.  WGSL leaves contraction and the
+ * rounding of `/` (2.5 ulp) to the shader compiler; the two modes are the two ends of that latitude:
+ *   LITERAL  one IEEE-754 binary32 operation per WGSL expression node, in source order; true division.
+ *            Bit-comparable with the oracle's "contract" flavour.
+ *   FUSED    (default) x*y+z contracted to one fma where the expression tree has that shape, vec3/f32 computed as
+ *            vec3 * (1/f32).  ~1.5x fewer instructions.  Bit-comparable with the oracle's "fused" flavour. */
+typedef enum bh_numeric_mode { BH_NUMERIC_LITERAL = 0, BH_NUMERIC_FUSED = 1 } bh_numeric_mode;
+int  bh_ctx_set_numeric_mode(bh_ctx *ctx, bh_numeric_mode mode);
+int  bh_ctx_get_numeric_mode(const bh_ctx *ctx);
+
 /* texture::Texture::from_bytes (src/renderer/texture.rs:10-80) minus the PNG decode: RGBA8 unorm
  * (no sRGB), bilinear, clamp-to-edge, one mip.  Copies rgba8 (w*h*4 bytes) to the device. */
 int  bh_ctx_set_texture(bh_ctx *ctx, bh_texture_slot slot, const uint8_t *rgba8, uint32_t w, uint32_t h);

@@ -96,25 +96,47 @@ typedef struct { bho_counters c; } tls_t;
 /* ------------------------------------------------------------------ vec helpers (CHOICE: WGSL built-ins
  * expanded left to right, one IEEE op per node) */
 static inline v3 V(float x, float y, float z) { v3 r = { x, y, z }; return r; }
+
+/* madd(a,b,c) = a*b + c.  LITERAL flavours: two IEEE operations (what a non-contracting WGSL compiler
+ * emits).  FUSED flavour: one fmaf — WGSL permits contracting x*y+z into fma (naga emits no
+ * NoContraction decoration), and real drivers do.  Every helper below is written through madd with
+ * the association order of the WGSL expression, so the literal flavours are unchanged by it:
+ * a*b + (-c) == a*b - c and (-a)*b + c == c - a*b exactly in IEEE arithmetic. */
+#if defined(BHO_FUSED)
+static inline float madd(float a, float b, float c) { return fmaf(a, b, c); }
+#else
+static inline float madd(float a, float b, float c) { return a * b + c; }
+#endif
+static inline float msub(float a, float b, float c) { return madd(a, b, -c); }     /* a*b - c */
+static inline float nmadd(float a, float b, float c) { return madd(-a, b, c); }    /* c - a*b */
+
 static inline v3 vadd(v3 a, v3 b) { return V(a.x + b.x, a.y + b.y, a.z + b.z); }
 static inline v3 vsub(v3 a, v3 b) { return V(a.x - b.x, a.y - b.y, a.z - b.z); }
 static inline v3 vmul(v3 a, v3 b) { return V(a.x * b.x, a.y * b.y, a.z * b.z); }
 static inline v3 vscale(v3 a, float s) { return V(a.x * s, a.y * s, a.z * s); }
 static inline v3 sscale(float s, v3 a) { return V(s * a.x, s * a.y, s * a.z); }
+/* vec3 / f32.  LITERAL: three IEEE divisions.  FUSED: multiply by the correctly rounded reciprocal
+ * (<= 1.5 ulp, inside WGSL's 2.5 ulp bound for `/`; what GPU drivers emit for vector/scalar). */
+#if defined(BHO_FUSED)
+static inline v3 vdivs(v3 a, float s) { const float r = 1.0f / s; return V(a.x * r, a.y * r, a.z * r); }
+#else
 static inline v3 vdivs(v3 a, float s) { return V(a.x / s, a.y / s, a.z / s); }
+#endif
 static inline v3 vneg(v3 a) { return V(-a.x, -a.y, -a.z); }
-static inline float vdot(v3 a, v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+static inline float vdot(v3 a, v3 b) { return madd(a.z, b.z, madd(a.y, b.y, a.x * b.x)); }
 static inline v3 vcross(v3 a, v3 b)
 {
-    return V(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+    return V(msub(a.y, b.z, a.z * b.y), msub(a.z, b.x, a.x * b.z), msub(a.x, b.y, a.y * b.x));
 }
+/* p + v*s and acc + s*k (the same thing; two spellings keep call sites readable) */
+static inline v3 vmadd(v3 v, float s, v3 p) { return V(madd(v.x, s, p.x), madd(v.y, s, p.y), madd(v.z, s, p.z)); }
 static inline float vlength(v3 a) { return sqrtf(vdot(a, a)); }
 static inline float vdistance(v3 a, v3 b) { return vlength(vsub(a, b)); }
 static inline v3 vnormalize(v3 a) { return vdivs(a, vlength(a)); }
 static inline v3 vmix(v3 a, v3 b, float t)   /* WGSL mix: e1*(1-e3) + e2*e3 */
 {
     float u = 1.0f - t;
-    return V(a.x * u + b.x * t, a.y * u + b.y * t, a.z * u + b.z * t);
+    return V(madd(b.x, t, a.x * u), madd(b.y, t, a.y * u), madd(b.z, t, a.z * u));
 }
 static inline v3 vmin(v3 a, v3 b) { return V(bho_min(a.x, b.x), bho_min(a.y, b.y), bho_min(a.z, b.z)); }
 static inline v3 vmax(v3 a, v3 b) { return V(bho_max(a.x, b.x), bho_max(a.y, b.y), bho_max(a.z, b.z)); }
@@ -126,13 +148,14 @@ static inline float smoothstep_f(float lo, float hi, float x)
 /* determinant(mat3x3(c0,c1,c2)) — CHOICE: cofactor expansion in GLM order */
 static inline float det3(v3 c0, v3 c1, v3 c2)
 {
-    return c0.x * (c1.y * c2.z - c2.y * c1.z)
-         - c1.x * (c0.y * c2.z - c2.y * c0.z)
-         + c2.x * (c0.y * c1.z - c1.y * c0.z);
+    const float m0 = msub(c1.y, c2.z, c2.y * c1.z);
+    const float m1 = msub(c0.y, c2.z, c2.y * c0.z);
+    const float m2 = msub(c0.y, c1.z, c1.y * c0.z);
+    return madd(c2.x, m2, nmadd(c1.x, m1, c0.x * m0));
 }
 static inline v3 mat3_mul(v3 c0, v3 c1, v3 c2, v3 v)   /* M*v = c0*v.x + c1*v.y + c2*v.z */
 {
-    return vadd(vadd(vscale(c0, v.x), vscale(c1, v.y)), vscale(c2, v.z));
+    return vmadd(c2, v.z, vmadd(c1, v.y, vscale(c0, v.x)));
 }
 
 /* ------------------------------------------------------------------ uniforms from raw bytes */
@@ -184,8 +207,8 @@ static inline v4 texel(const bho_texture *t, int x, int y)
 static v4 sample_bilinear(const bho_texture *t, float u, float v, tls_t *tls)
 {
     tls->c.tex_samples++;
-    float x = u * (float)t->w - 0.5f;
-    float y = v * (float)t->h - 0.5f;
+    float x = msub(u, (float)t->w, 0.5f);
+    float y = msub(v, (float)t->h, 0.5f);
     float x0 = floorf(x), y0 = floorf(y);
     float fx = x - x0, fy = y - y0;
     int ix0 = tex_index(x0, t->w), ix1 = tex_index(x0 + 1.0f, t->w);
@@ -193,9 +216,9 @@ static v4 sample_bilinear(const bho_texture *t, float u, float v, tls_t *tls)
     v4 t00 = texel(t, ix0, iy0), t10 = texel(t, ix1, iy0);
     v4 t01 = texel(t, ix0, iy1), t11 = texel(t, ix1, iy1);
     float ux = 1.0f - fx, uy = 1.0f - fy;
-    v4 top = { t00.r * ux + t10.r * fx, t00.g * ux + t10.g * fx, t00.b * ux + t10.b * fx, t00.a * ux + t10.a * fx };
-    v4 bot = { t01.r * ux + t11.r * fx, t01.g * ux + t11.g * fx, t01.b * ux + t11.b * fx, t01.a * ux + t11.a * fx };
-    v4 o = { top.r * uy + bot.r * fy, top.g * uy + bot.g * fy, top.b * uy + bot.b * fy, top.a * uy + bot.a * fy };
+    v4 top = { madd(t10.r, fx, t00.r * ux), madd(t10.g, fx, t00.g * ux), madd(t10.b, fx, t00.b * ux), madd(t10.a, fx, t00.a * ux) };
+    v4 bot = { madd(t11.r, fx, t01.r * ux), madd(t11.g, fx, t01.g * ux), madd(t11.b, fx, t01.b * ux), madd(t11.a, fx, t01.a * ux) };
+    v4 o = { madd(bot.r, fy, top.r * uy), madd(bot.g, fy, top.g * uy), madd(bot.b, fy, top.b * uy), madd(bot.a, fy, top.a * uy) };
     return o;
 }
 
@@ -258,8 +281,8 @@ static render_state hit_sphere(ray_t ray, float radius, v3 center, v3 color, flo
     v3 oc = vsub(ray.position, center);
     float a = vdot(ray.direction, ray.direction);
     float b = 2.0f * vdot(oc, ray.direction);
-    float c = vdot(oc, oc) - radius * radius;
-    float discriminant = b * b - 4.0f * a * c;
+    float c = nmadd(radius, radius, vdot(oc, oc));
+    float discriminant = msub(b, b, 4.0f * a * c);
     if (discriminant > 0.0f) {
         float t1 = (-b - sqrtf(discriminant)) / (2.0f * a);
         float t2 = (-b + sqrtf(discriminant)) / (2.0f * a);
@@ -267,7 +290,7 @@ static render_state hit_sphere(ray_t ray, float radius, v3 center, v3 color, flo
         if (t1 > t_min && t1 < t_max) t_closest = t1;
         if (t2 > t_min && t2 < t_max && t2 < t_closest) t_closest = t2;
         if (t_closest < t_max && t_closest > t_min) {
-            v3 ip = vadd(ray.position, sscale(t_closest, ray.direction));
+            v3 ip = vmadd(ray.direction, t_closest, ray.position);
             rs.color = color;
             rs.opacity = 1.0f;
             rs.t = t_closest;
@@ -288,7 +311,7 @@ static render_state hit_torus2d(ray_t ray, float inner, float outer, v3 pos, v3 
     float t = vdot(dist, normal) / denom;
     if (t < t_max && t > t_min) {
         rs.normal = denom < 0.0f ? vneg(normal) : normal;
-        v3 ip = vadd(ray.position, vscale(ray.direction, t));
+        v3 ip = vmadd(ray.direction, t, ray.position);
         float dc = vdistance(pos, ip);
         if (dc >= inner && dc <= outer) {
             rs.color = V(1.0f, 1.0f, 1.0f);
@@ -310,7 +333,7 @@ static render_state hit_black_hole(const ctx_t *cx, ray_t ray, float t_min, floa
 
     if (disk_hit.hit && disk_hit.t < rs.t) {
         rs = disk_hit;
-        v3 intersection = vadd(ray.position, vscale(ray.direction, rs.t));
+        v3 intersection = vmadd(ray.direction, rs.t, ray.position);
         float dist = vdistance(bh->position, intersection);
         /* disk_displacement (ray.wgsl:618) is dead */
         float disk_density = 1.0f - vlength(vdivs(intersection, bh->outer_radius));
@@ -326,13 +349,11 @@ static render_state hit_black_hole(const ctx_t *cx, ray_t ray, float t_min, floa
             v3 relative_pos = vdivs(vsub(intersection, bh->position), bh->outer_radius);
             v3 rotated_pos = mat3_mul(bh->m0, bh->m1, bh->m2, relative_pos);
             float angle = -bho_atan2(rotated_pos.z, rotated_pos.x);
-            float arg = angle + cx->details.time * bh->rotation_speed;
-            float u = bho_sin(arg) * r;
-            float v = bho_cos(arg) * r;
-            u = (u + 1.0f) / 2.0f;
-            v = (v + 1.0f) / 2.0f;
+            float arg = madd(cx->details.time, bh->rotation_speed, angle);
+            float u = madd(bho_sin(arg), r, 1.0f) / 2.0f;
+            float v = madd(bho_cos(arg), r, 1.0f) / 2.0f;
             v4 dc = sample_bilinear(&cx->scene->disk, u, v, tls);
-            rs.opacity *= bho_clamp(0.7f + dc.a * 0.5f, 0.0f, 1.0f);
+            rs.opacity *= bho_clamp(madd(dc.a, 0.5f, 0.7f), 0.0f, 1.0f);
             rs.color = vmul(rs.color, V(dc.r * dc.a, dc.g * dc.a, dc.b * dc.a));
         }
 
@@ -391,10 +412,9 @@ static render_state hit_triangle(ray_t ray, float t_min, float t_max, v3 pa, v3 
 
     float t = det3(vsub(pa, ray.position), vsub(pa, pb), vsub(pa, pc)) / denominator;
     if (t > t_min && t < t_max) {
-        v3 normal = vadd(vadd(sscale(1.0f - u - v, n1), sscale(u, n2)), sscale(v, n3));
-        v3 h = vscale(vneg(normal), 0.5f);
+        v3 normal = vmadd(n3, v, vmadd(n2, u, sscale(1.0f - u - v, n1)));
         rs.normal = n;
-        rs.color = V(h.x + 0.5f, h.y + 0.5f, h.z + 0.5f);
+        rs.color = V(madd(-normal.x, 0.5f, 0.5f), madd(-normal.y, 0.5f, 0.5f), madd(-normal.z, 0.5f, 0.5f));
         rs.opacity = 1.0f;
         rs.t = t;
         rs.hit = 1;
@@ -524,33 +544,32 @@ static rk_state_t next_ray_rk(const ctx_t *cx, rk_state_t st, tls_t *tls)
     /* Q5: the accept loop body runs once; e_max > 1 would spin forever in the reference */
     float h = st.h;
     v3 k_1 = dydx;
-    v3 k_2 = accel(cx, vadd(ray.position, vscale(sscale(A21, k_1), h)), h2, r5);
-    v3 k_3 = accel(cx, vadd(ray.position, vscale(vadd(sscale(A31, k_1), sscale(A32, k_2)), h)), h2, r5);
+    v3 k_2 = accel(cx, vmadd(sscale(A21, k_1), h, ray.position), h2, r5);
+    v3 k_3 = accel(cx, vmadd(vmadd(k_2, A32, sscale(A31, k_1)), h, ray.position), h2, r5);
     /* Q4: a_43 multiplies k_2 */
-    v3 k_4 = accel(cx, vadd(ray.position, vscale(vadd(vadd(sscale(A41, k_1), sscale(A42, k_2)), sscale(A43, k_2)), h)), h2, r5);
-    v3 k_5 = accel(cx, vadd(ray.position, vscale(vadd(vadd(vadd(sscale(A51, k_1), sscale(A52, k_2)), sscale(A53, k_3)), sscale(A54, k_4)), h)), h2, r5);
-    v3 k_6 = accel(cx, vadd(ray.position, vscale(vadd(vadd(vadd(vadd(sscale(A61, k_1), sscale(A62, k_2)), sscale(A63, k_3)), sscale(A64, k_4)), sscale(A65, k_5)), h)), h2, r5);
+    v3 k_4 = accel(cx, vmadd(vmadd(k_2, A43, vmadd(k_2, A42, sscale(A41, k_1))), h, ray.position), h2, r5);
+    v3 k_5 = accel(cx, vmadd(vmadd(k_4, A54, vmadd(k_3, A53, vmadd(k_2, A52, sscale(A51, k_1)))), h, ray.position), h2, r5);
+    v3 k_6 = accel(cx, vmadd(vmadd(k_5, A65, vmadd(k_4, A64, vmadd(k_3, A63, vmadd(k_2, A62, sscale(A61, k_1))))), h, ray.position), h2, r5);
 
     v3 esum = sscale((float)(B1 - BA1), k_1);
-    esum = vadd(esum, sscale((float)(B2 - BA2), k_2));
-    esum = vadd(esum, sscale((float)(B3 - BA3), k_3));
-    esum = vadd(esum, sscale((float)(B4 - BA4), k_4));
-    esum = vadd(esum, sscale((float)(B5 - BA5), k_5));
-    esum = vadd(esum, sscale((float)(B6 - BA6), k_6));
+    esum = vmadd(k_2, (float)(B2 - BA2), esum);
+    esum = vmadd(k_3, (float)(B3 - BA3), esum);
+    esum = vmadd(k_4, (float)(B4 - BA4), esum);
+    esum = vmadd(k_5, (float)(B5 - BA5), esum);
+    esum = vmadd(k_6, (float)(B6 - BA6), esum);
     v3 e = sscale(h, esum);
     /* yscal = 1, eps = 1: x/1 == x */
     st.e_max = bho_max(bho_max(fabsf(e.x), fabsf(e.y)), fabsf(e.z));
     if (!(st.e_max <= 1.0f)) tls->c.rk_reject++;
 
     v3 dsum = sscale((float)BA1, k_1);
-    dsum = vadd(dsum, sscale((float)BA2, k_2));
-    dsum = vadd(dsum, sscale((float)BA3, k_3));
-    dsum = vadd(dsum, sscale((float)BA4, k_4));
-    dsum = vadd(dsum, sscale((float)BA5, k_5));
-    dsum = vadd(dsum, sscale((float)BA6, k_6));
-    st.ray.direction = vadd(st.ray.direction, sscale(st.h, dsum));
-    st.ray.direction = vnormalize(st.ray.direction);
-    st.ray.position = vadd(st.ray.position, vscale(ray.direction, st.h));      /* Q6: OLD direction */
+    dsum = vmadd(k_2, (float)BA2, dsum);
+    dsum = vmadd(k_3, (float)BA3, dsum);
+    dsum = vmadd(k_4, (float)BA4, dsum);
+    dsum = vmadd(k_5, (float)BA5, dsum);
+    dsum = vmadd(k_6, (float)BA6, dsum);
+    st.ray.direction = vnormalize(vmadd(dsum, st.h, st.ray.direction));
+    st.ray.position = vmadd(ray.direction, st.h, st.ray.position);                 /* Q6: OLD direction */
 
     if (st.e_max > 0.00002f) st.h *= 0.9f * bho_pow(st.e_max, -0.001f);
     else st.h *= 1.0001f;
@@ -563,9 +582,8 @@ static ray_t next_ray_euler(const ctx_t *cx, ray_t ray, float step_size)
     float h2 = bho_pow2(vlength(vcross(ray.position, ray.direction)));
     float dist = vlength(vsub(ray.position, cx->bh.position));
     float r5 = bho_pow5(dist);
-    ray.direction = vadd(ray.direction, vscale(accel(cx, ray.position, h2, r5), step_size));
-    ray.direction = vnormalize(ray.direction);
-    ray.position = vadd(ray.position, vscale(ray.direction, step_size));   /* Q8: NEW direction */
+    ray.direction = vnormalize(vmadd(accel(cx, ray.position, h2, r5), step_size, ray.direction));
+    ray.position = vmadd(ray.direction, step_size, ray.position);          /* Q8: NEW direction */
     return ray;
 }
 
@@ -574,7 +592,7 @@ static inline void sky_uv(v3 dir, float *u, float *v)
 {
     /* cartesian_to_spherical(dir.xzy) then the uv of ray.wgsl:586 / sky.wgsl:21 (Q19) */
     v3 c = V(dir.x, dir.z, dir.y);
-    float theta = bho_atan2(sqrtf(c.x * c.x + c.y * c.y), c.z);
+    float theta = bho_atan2(sqrtf(madd(c.y, c.y, c.x * c.x)), c.z);
     float phi = bho_atan2(c.y, c.x);
     float uu = (phi + 2.6f * PI_F) / (2.0f * PI_F);
     float vv = (PI_F - theta) / PI_F;
@@ -636,7 +654,7 @@ static trace_out trace_ray(const ctx_t *cx, ray_t ray, tls_t *tls)
             render_state hs = hit_sphere(prev_ray, bh_radius, bh_position, V(0, 0, 0), t_min, t_max);   /* Q10 */
             if (!hs.hit && !rs.hit) break;
             if (hs.hit && hs.t < rs.t) {
-                curr_ray.position = vadd(curr_ray.position, vscale(curr_ray.direction, hs.t));
+                curr_ray.position = vmadd(curr_ray.direction, hs.t, curr_ray.position);
                 relativity = 1;
             } else {
                 closest = rs;
@@ -644,11 +662,11 @@ static trace_out trace_ray(const ctx_t *cx, ray_t ray, tls_t *tls)
         }
 
         if (closest.hit) {
-            curr_ray.position = vadd(curr_ray.position, vscale(prev_ray.direction, closest.t));   /* Q11 */
+            curr_ray.position = vmadd(prev_ray.direction, closest.t, curr_ray.position);          /* Q11 */
             v3 cc = V(bho_clamp(closest.color.x, 0.0f, 1.0f), bho_clamp(closest.color.y, 0.0f, 1.0f),
                       bho_clamp(closest.color.z, 0.0f, 1.0f));
             float w = color_amount * closest.opacity;
-            color = vadd(color, sscale(w, cc));
+            color = vmadd(cc, w, color);
             color_amount *= 1.0f - closest.opacity;
             hit = 1;
             if (closest.tri >= 0) out.hit_tri = closest.tri;
@@ -662,7 +680,7 @@ static trace_out trace_ray(const ctx_t *cx, ray_t ray, tls_t *tls)
             sky_uv(curr_ray.direction, &u, &v);
             v4 s = sample_bilinear(&cx->scene->sky, u, v, tls);
             v3 miss = V(bho_pow4(s.r), bho_pow4(s.g), bho_pow4(s.b));
-            color = vadd(color, sscale(color_amount, miss));
+            color = vmadd(miss, color_amount, color);
         }
         out.r = color.x; out.g = color.y; out.b = color.z; out.a = 1.0f;
         return out;
@@ -682,7 +700,7 @@ static ray_t create_ray(const ctx_t *cx, int px, int py, int sw, int sh)
     v3 right = vnormalize(vcross(cx->camera.forward, plane_up));
     v3 up = vnormalize(vcross(cx->camera.forward, right));
     float fov_factor = 1.0f / bho_tan(cx->camera.fov / 2.0f);
-    v3 d = vadd(vadd(sscale(posx, right), sscale(posy, up)), vscale(cx->camera.forward, fov_factor));  /* Q21 */
+    v3 d = vmadd(cx->camera.forward, fov_factor, vmadd(up, posy, sscale(posx, right)));               /* Q21 */
     ray_t r; r.position = cx->camera.position; r.direction = vnormalize(d);
     return r;
 }
@@ -1235,7 +1253,9 @@ void bho_kat_math_array(int fn, const float *a, const float *b, float *out, int6
 }
 int bho_flavour(void)
 {
-#if defined(BHO_FLAVOUR_CONTRACT)
+#if defined(BHO_FLAVOUR_CONTRACT) && defined(BHO_FUSED)
+    return 2;
+#elif defined(BHO_FLAVOUR_CONTRACT)
     return 1;
 #else
     return 0;

@@ -3,8 +3,11 @@
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 import this module.  The product package (bhusie_b200/) never does.
 
-Flavours (see bho_math.h): "strict" = glibc libm transcendentals (neutral; also the CPU
-baseline), "contract" = det-math, bit-comparable with the CUDA kernel.
+Flavours (see bho_math.h and the madd/vdivs helpers in bh_oracle.c):
+  "strict"    glibc libm transcendentals, one IEEE op per WGSL expression node (neutral; also the CPU baseline)
+  "contract"  det-math transcendentals, same literal op order -> bit-comparable with the kernel's LITERAL mode
+  "fused"     det-math + explicit fma contraction + reciprocal-multiply for vec/scalar division
+              -> bit-comparable with the kernel's FUSED mode (the fast default)
 """
 from __future__ import annotations
 
@@ -36,9 +39,12 @@ class _Counters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in COUNTER_FIELDS]
 
 
+FLAVOURS = ("strict", "contract", "fused")
+
+
 def build(force: bool = False) -> None:
     """Compile both flavours with oracle/Makefile (gcc, -ffp-contract=off, OpenMP)."""
-    libs = [os.path.join(_HERE, "lib", f"libbh_oracle_{f}.so") for f in ("strict", "contract")]
+    libs = [os.path.join(_HERE, "lib", f"libbh_oracle_{f}.so") for f in FLAVOURS]
     srcs = [os.path.join(_HERE, n) for n in ("bh_oracle.c", "bho_math.h", "Makefile")]
     stale = force or any(not os.path.exists(l) for l in libs) or \
         max(os.path.getmtime(s) for s in srcs) > min(os.path.getmtime(l) for l in libs)
@@ -50,7 +56,7 @@ _LIBS: dict[str, C.CDLL] = {}
 
 
 def _lib(flavour: str) -> C.CDLL:
-    if flavour not in ("strict", "contract"):
+    if flavour not in FLAVOURS:
         raise ValueError(flavour)
     if flavour not in _LIBS:
         path = os.path.join(_HERE, "lib", f"libbh_oracle_{flavour}.so")
@@ -71,7 +77,7 @@ def _lib(flavour: str) -> C.CDLL:
             getattr(lib, f"bho_kat_{n}").argtypes = [C.c_float]
         lib.bho_kat_f16.restype = C.c_uint16
         lib.bho_kat_f16.argtypes = [C.c_float]
-        assert lib.bho_flavour() == (1 if flavour == "contract" else 0)
+        assert lib.bho_flavour() == FLAVOURS.index(flavour)
         _LIBS[flavour] = lib
     return _LIBS[flavour]
 

@@ -19,27 +19,36 @@ pytestmark = pytest.mark.gpu
 
 AUX = P.AUX_HIT | P.AUX_STEPS | P.AUX_CLASS
 TOL = 1e-4                 # BASELINE.json north_star: 1e-4 per RGBA channel
-STRICT_OUTLIER_FRAC = 2e-3  # pixels allowed beyond TOL vs the libm flavour (chaotic rays near the photon sphere / star edges)
+STRICT_OUTLIER_FRAC = 3e-3  # pixels allowed beyond TOL vs the libm flavour: discontinuities (disk/mesh/horizon edges, star edges)
+                            # flip under ANY rounding change; measured 6e-5 (literal) .. 1e-3 (fused) on the test frames
 
 
-@pytest.fixture(scope="module")
-def ctx_small(small_scene):
+MODES = [pytest.param(P.NUMERIC_LITERAL, id="literal"), pytest.param(P.NUMERIC_FUSED, id="fused")]
+
+
+def fl(ctx):
+    """The oracle flavour the context's numeric mode is bit-comparable with."""
+    return P.ORACLE_FLAVOUR_OF_MODE[ctx.numeric_mode]
+
+
+@pytest.fixture(scope="module", params=MODES)
+def ctx_small(request, small_scene):
     tex, blob, _ = small_scene
-    ctx = P.Context(0)
+    ctx = P.Context(0, numeric_mode=request.param)
     ctx.set_textures(tex)
     ctx.upload_models(blob)
     yield ctx
     ctx.close()
 
 
-@pytest.fixture(scope="module")
-def real_scene(oracle):
+@pytest.fixture(scope="module", params=MODES)
+def real_scene(request, oracle):
     tex, src = assets.load_textures()
     if assets.have_lucy():
         blob, info = P.load_obj_model(assets.lucy_path())
     else:
         blob, info = P.model_from_arrays(*assets.uv_sphere())
-    ctx = P.Context(0)
+    ctx = P.Context(0, numeric_mode=request.param)
     ctx.set_textures(tex)
     ctx.upload_models(blob)
     osc = oracle.OracleScene(tex["color"], tex["disk"], tex["sky"], blob)
@@ -72,7 +81,7 @@ def assert_close_to_strict(dev, strict, what=""):
     d = np.abs(dev["rgba"].astype(np.float64) - strict.rgba.astype(np.float64))
     bad = (d > TOL).any(axis=2).mean()
     assert bad <= STRICT_OUTLIER_FRAC, f"{what}: {bad:.4%} of pixels beyond {TOL} vs libm oracle (max {d.max():.3g})"
-    assert (dev["hit"] == strict.hit).mean() >= 0.999 and (dev["steps"] == strict.steps).mean() >= 0.999
+    assert (dev["hit"] == strict.hit).mean() >= 0.999 and (dev["steps"] == strict.steps).mean() >= 0.998
 
 
 # ------------------------------------------------------------------ det-math: device == oracle contract flavour, bit for bit
@@ -92,7 +101,7 @@ def test_detmath_bit_exact(ctx_small, oracle):
         a = a.astype(np.float32)
         b = None if b is None else b.astype(np.float32)
         dev = ctx_small.math_probe(fn, a, b)
-        ora = oracle.math_array(fn, a, b, flavour="contract")
+        ora = oracle.math_array(fn, a, b, flavour=fl(ctx_small))
         same = (bits(dev) == bits(ora)) | (np.isnan(dev) & np.isnan(ora))
         assert same.all(), (fn, a[~same][:5], None if b is None else b[~same][:5], dev[~same][:5], ora[~same][:5])
 
@@ -105,7 +114,7 @@ def test_small_scene_bit_exact(ctx_small, oracle, small_oracle_scene, method, ca
     det = U.RayDetails(integration_method=method, model_count=1, time=1.25)
     w, h = 96, 54
     rp, dev, st = render(ctx_small, w, h, cam, hole, det)
-    ora = oracle.ray_pass(small_oracle_scene, w, h, cam.uniform(), hole.uniform(), det.uniform(), flavour="contract")
+    ora = oracle.ray_pass(small_oracle_scene, w, h, cam.uniform(), hole.uniform(), det.uniform(), flavour=fl(ctx_small))
     assert_bit_exact(dev, ora, f"method {method} cam {campos}")
     assert_stats(st, ora.counters)
     strict = oracle.ray_pass(small_oracle_scene, w, h, cam.uniform(), hole.uniform(), det.uniform(), flavour="strict")
@@ -135,7 +144,7 @@ def test_parameter_variants_bit_exact(ctx_small, oracle, small_oracle_scene, var
             blob = osc.models.copy()
             blob[12:16].view(np.int32)[0] = 0
             osc = oracle.OracleScene(osc.color, osc.disk, osc.sky, blob)
-        ora = oracle.ray_pass(osc, w, h, cam.uniform(), hole.uniform(), det.uniform(), flavour="contract")
+        ora = oracle.ray_pass(osc, w, h, cam.uniform(), hole.uniform(), det.uniform(), flavour=fl(ctx_small))
         assert_bit_exact(dev, ora, variant)
         assert_stats(st, ora.counters)
         if variant == "moved_hole":
@@ -160,7 +169,7 @@ def test_ragged_sizes_bit_exact(ctx_small, oracle, small_oracle_scene):
     cam, hole, det = U.Camera(), U.BlackHole(), U.RayDetails(integration_method=1, model_count=1)
     for (w, h) in ((2, 2), (9, 5), (33, 7), (7, 33), (65, 37)):
         rp, dev, st = render(ctx_small, w, h, cam, hole, det)
-        ora = oracle.ray_pass(small_oracle_scene, w, h, cam.uniform(), hole.uniform(), det.uniform(), flavour="contract")
+        ora = oracle.ray_pass(small_oracle_scene, w, h, cam.uniform(), hole.uniform(), det.uniform(), flavour=fl(ctx_small))
         assert_bit_exact(dev, ora, f"{w}x{h}")
         assert_stats(st, ora.counters)
         rp.close()
@@ -177,14 +186,14 @@ def test_pyramid_and_sky_bit_exact(ctx_small, oracle, small_oracle_scene, thr):
     prev = None
     for rp in pyr.levels:
         dev = rp.read()
-        ora = oracle.ray_pass(small_oracle_scene, rp.width, rp.height, cam.uniform(), hole.uniform(), det.uniform(), prev=prev, flavour="contract")
+        ora = oracle.ray_pass(small_oracle_scene, rp.width, rp.height, cam.uniform(), hole.uniform(), det.uniform(), prev=prev, flavour=fl(ctx_small))
         assert_bit_exact(dev, ora, f"level {rp.width}x{rp.height}")
         assert_stats(rp.stats(), ora.counters)
         prev = ora.rgba
     if thr == 0.08:
         assert pyr.levels[2].stats()["px_interp"] > 10000
     sky32 = pyr.sky.read()
-    o32, o16, cnt = oracle.sky_pass(small_oracle_scene, prev, flavour="contract")
+    o32, o16, cnt = oracle.sky_pass(small_oracle_scene, prev, flavour=fl(ctx_small))
     assert np.array_equal(bits(sky32), bits(o32))
     assert np.all(sky32[..., 3] == 1)
     sky16 = P.SkyPipeline(ctx_small, pyr.levels[-1], P.SKY_RGBA16F)       # the reference's Rgba16Float target
@@ -200,7 +209,7 @@ def test_c1_config(real_scene, oracle):
     ctx, osc, src = real_scene
     cam, hole, det = U.Camera(), U.BlackHole(), U.RayDetails(integration_method=0, model_count=0)
     rp, dev, st = render(ctx, 256, 256, cam, hole, det)
-    ora = oracle.ray_pass(osc, 256, 256, cam.uniform(), hole.uniform(), det.uniform(), flavour="contract")
+    ora = oracle.ray_pass(osc, 256, 256, cam.uniform(), hole.uniform(), det.uniform(), flavour=fl(ctx))
     assert_bit_exact(dev, ora, "C1")
     assert_stats(st, ora.counters)
     assert_close_to_strict(dev, oracle.ray_pass(osc, 256, 256, cam.uniform(), hole.uniform(), det.uniform(), flavour="strict"), "C1")
@@ -214,7 +223,7 @@ def test_mesh_scene_hit_indices(real_scene, oracle, campos, fwd):
     cam, hole, det = U.Camera(position=campos, forward=fwd), U.BlackHole(), U.RayDetails(integration_method=1, model_count=1)
     w, h = 384, 216
     rp, dev, st = render(ctx, w, h, cam, hole, det)
-    ora = oracle.ray_pass(osc, w, h, cam.uniform(), hole.uniform(), det.uniform(), flavour="contract")
+    ora = oracle.ray_pass(osc, w, h, cam.uniform(), hole.uniform(), det.uniform(), flavour=fl(ctx))
     assert_bit_exact(dev, ora, f"mesh cam {campos}")
     assert_stats(st, ora.counters)
     assert (dev["hit"] >= 0).sum() > 500
@@ -234,11 +243,11 @@ def test_reference_pyramid_first_levels(real_scene, oracle):
     prev = None
     for rp in pyr.levels:
         dev = rp.read()
-        ora = oracle.ray_pass(osc, rp.width, rp.height, cam.uniform(), hole.uniform(), det.uniform(), prev=prev, flavour="contract")
+        ora = oracle.ray_pass(osc, rp.width, rp.height, cam.uniform(), hole.uniform(), det.uniform(), prev=prev, flavour=fl(ctx))
         assert_bit_exact(dev, ora, f"level {rp.width}x{rp.height}")
         prev = ora.rgba
     assert pyr.levels[2].stats()["px_interp"] > 50000
-    _, o16, _ = oracle.sky_pass(osc, prev, flavour="contract")
+    _, o16, _ = oracle.sky_pass(osc, prev, flavour=fl(ctx))
     assert np.array_equal(pyr.sky.read().view(np.uint16), o16)
     pyr.close()
 
@@ -273,7 +282,7 @@ def test_tiled_pyramid_level(ctx_small, oracle, small_oracle_scene):
     l0 = P.RayPipeline(ctx_small, 32, 18)
     l0.pass_(cam, hole, det)
     prev = l0.read()["rgba"]
-    ora = oracle.ray_pass(small_oracle_scene, 94, 52, cam.uniform(), hole.uniform(), det.uniform(), prev=prev, flavour="contract")
+    ora = oracle.ray_pass(small_oracle_scene, 94, 52, cam.uniform(), hole.uniform(), det.uniform(), prev=prev, flavour=fl(ctx_small))
     lay = BandLayout(52, 4, 3)
     for rank in range(3):
         t = P.RayPipeline(ctx_small, 94, 52, l0, aux=AUX)
@@ -349,7 +358,7 @@ def test_full_size_properties(real_scene, oracle, w, h, mc):
     rp, dev, st = render(ctx, w, h, cam, hole, det, aux=P.AUX_HIT | P.AUX_STEPS)
     rows = sorted({0, h // 7, h // 3, h // 2 - 1, h // 2, (2 * h) // 3, h - 1})
     for y in rows:                                                   # (a)
-        ora = oracle.ray_pass(osc, w, h, cam.uniform(), hole.uniform(), det.uniform(), rows=(y, y + 1), flavour="contract")
+        ora = oracle.ray_pass(osc, w, h, cam.uniform(), hole.uniform(), det.uniform(), rows=(y, y + 1), flavour=fl(ctx))
         assert np.array_equal(bits(dev["rgba"][y]), bits(ora.rgba[y])), f"row {y}"
         assert np.array_equal(dev["hit"][y], ora.hit[y]) and np.array_equal(dev["steps"][y], ora.steps[y])
     assert st["ray_steps"] == int(dev["steps"].sum(dtype=np.int64))  # (c)
