@@ -70,7 +70,8 @@ SYMBOLS = {
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    """bhusie_b200/lib/libbhray.so; BHRAY_LIB overrides it with another build of the same sources (tuning runs)."""
+    return os.environ.get("BHRAY_LIB") or _build.LIB_PATH
 
 
 def load() -> C.CDLL:

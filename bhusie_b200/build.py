@@ -43,12 +43,14 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force: bool = False, verbose: bool = False, extra: list[str] | None = None) -> str:
-    if not force and not is_stale():
+def build_library(force: bool = False, verbose: bool = False, extra: list[str] | None = None, out: str | None = None) -> str:
+    """Builds libbhray.so.  `extra`/`out` build an experimental variant (tuning runs) beside the product library."""
+    out = out or LIB_PATH
+    if not force and out == LIB_PATH and not is_stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     cmd = [nvcc_path(), *NVCC_FLAGS, *(extra or []), "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++",
-           "-o", LIB_PATH, *[os.path.join(CSRC, s) for s in SOURCES]]
+           "-o", out, *[os.path.join(CSRC, s) for s in SOURCES]]
     if verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
         print(" ".join(cmd))
@@ -57,7 +59,7 @@ def build_library(force: bool = False, verbose: bool = False, extra: list[str] |
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libbhray.so")
-    return LIB_PATH
+    return out
 
 
 if __name__ == "__main__":
