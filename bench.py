@@ -67,7 +67,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -185,7 +185,8 @@ def run_ours(args):
 
     W, H = args.width, args.height
     tex, tex_src, blob, mesh_src, mesh_info = load_scene()
-    ctx = P.Context(local_rank)
+    mode = {"literal": P.NUMERIC_LITERAL, "fused": P.NUMERIC_FUSED}[args.numeric_mode]
+    ctx = P.Context(local_rank, numeric_mode=mode)
     ctx.set_textures(tex)
     ctx.upload_models(blob)
     cam, hole = U.Camera(), U.BlackHole()
@@ -246,10 +247,15 @@ def run_ours(args):
     def step_e2e():
         flush.zero_()
         ctx.upload_models_async(pinned_model.data_ptr(), pinned_model.numel(), stream)
-        frame.render(cam, hole, det, stream)
-        if rank == 0:
-            host_frame.copy_(frame.frame_tensor(), non_blocking=True)
-        stream.synchronize()
+        if world == 1:
+            # public API: pass + read-back, the D2H of each row band overlapping the tracing of the next
+            frame.pipeline.pass_to_host(cam, hole, det, host_frame.data_ptr(), args.e2e_chunks, stream)
+            frame.pipeline.sync()
+        else:
+            frame.render(cam, hole, det, stream)
+            if rank == 0:
+                host_frame.copy_(frame.frame_tensor(), non_blocking=True)
+            stream.synchronize()
 
     for _ in range(max(1, min(args.warmup, 2))):
         step_e2e()
@@ -274,11 +280,12 @@ def run_ours(args):
         abytes = algorithmic_bytes(local, n_px_local)
         achieved = abytes / (kernel_ms * 1e-3) / 1e9
         traffic = None
+        # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel on this workload
         prof = os.path.join(ROOT, "profiles", "trace_kernel_dram.json")
-        if os.path.exists(prof):
+        if os.path.exists(prof) and (W, H) == (3840, 2160) and world == 1:
             try:
                 with open(prof) as f:
-                    traffic = json.load(f).get("dram_bytes_per_launch")
+                    traffic = json.load(f).get(args.numeric_mode, {}).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
         fp32_peak_tflops = 148 * 128 * 2 * (peak_json.get("sm_max_mhz", 1965.0) * 1e6) / 1e12
@@ -291,10 +298,15 @@ def run_ours(args):
                        "integrator": "cash-karp-rk", "step_size": 0.15, "max_iterations": 2000, "triangles": mesh_info.get("triangle_count"),
                        "bvh_nodes": mesh_info.get("nodes_used"), "tiling": f"cyclic bands of {frame.band_rows} rows over {world} rank(s)",
                        "l2_flush": "256 MiB memset before every step, inside the timed region",
-                       "ray_steps_per_frame": total["ray_steps"], "numerics": "strict contract: --fmad=false, IEEE div/sqrt, det-math"},
+                       "ray_steps_per_frame": total["ray_steps"],
+                       "numerics": ("FUSED: explicit fma contraction + reciprocal-multiply, det-math transcendentals (bit-exact vs oracle 'fused')"
+                                    if mode == P.NUMERIC_FUSED else
+                                    "LITERAL: one IEEE f32 op per WGSL node, det-math transcendentals (bit-exact vs oracle 'contract')")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pinned_model.numel() + 196),
                     "d2h_bytes_per_step": int(W * H * 16), "ms_per_step": 1000.0 * e2e_s / args.steps, "fps": args.steps / e2e_s,
-                    "frame_checksum": checksum},
+                    "frame_checksum": checksum,
+                    "path": (f"bh_ctx_upload_models_async + bh_ray_pipeline_pass_to_host({args.e2e_chunks} bands, D2H overlapped) + sync"
+                             if world == 1 else "upload_models_async + tiled pass + NCCL gather + D2H of the assembled frame")},
             "gpu_launches": int(args.steps * 1),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
@@ -325,12 +337,14 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--height", type=int, default=2160)
     ap.add_argument("--band-rows", type=int, default=8)
+    ap.add_argument("--numeric-mode", default="fused", choices=["fused", "literal"])
+    ap.add_argument("--e2e-chunks", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--allow-short-warmup", action="store_true", help="profiling runs only (ncu); numbers from such runs are not bench values")
     args = ap.parse_args()

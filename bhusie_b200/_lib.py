@@ -51,6 +51,8 @@ SYMBOLS = {
     "bh_ray_pipeline_enable_aux": (C.c_int, [_VP, _U32]),
     "bh_ray_pipeline_bind_output": (C.c_int, [_VP, _VP]),
     "bh_ray_pipeline_pass": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
+    "bh_ray_pipeline_pass_to_host": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _U32, _VP]),
+    "bh_ray_pipeline_sync": (C.c_int, [_VP]),
     "bh_ray_pipeline_output": (_VP, [_VP]),
     "bh_ray_pipeline_width": (_U32, [_VP]),
     "bh_ray_pipeline_height": (_U32, [_VP]),

@@ -73,6 +73,10 @@ struct bh_ray_pipeline {
     unsigned int *queue = nullptr;
     cudaStream_t last_stream = nullptr;
     bool ran = false;
+    cudaStream_t copy_stream = nullptr;              // chunked read-back (bh_ray_pipeline_pass_to_host)
+    cudaEvent_t chunk_done[16] = {};
+    cudaEvent_t copy_done = nullptr;
+    bool copy_pending = false;
     float4 *out() const { return bound_out ? bound_out : own_out; }
 };
 
@@ -255,6 +259,12 @@ void bh_ray_pipeline_destroy(bh_ray_pipeline *p)
     if (!p) return;
     cudaSetDevice(p->ctx->device);
     if (p->ran) cudaStreamSynchronize(p->last_stream);
+    if (p->copy_stream) {
+        cudaStreamSynchronize(p->copy_stream);
+        for (auto &e : p->chunk_done) if (e) cudaEventDestroy(e);
+        if (p->copy_done) cudaEventDestroy(p->copy_done);
+        cudaStreamDestroy(p->copy_stream);
+    }
     for (void *q : { (void *)p->own_out, (void *)p->aux_hit, (void *)p->aux_steps, (void *)p->aux_class, (void *)p->stats, (void *)p->work, (void *)p->queue })
         if (q) cudaFree(q);
     delete p;
@@ -293,25 +303,19 @@ int bh_ray_pipeline_bind_output(bh_ray_pipeline *p, void *device_rgba32f)
     return BH_OK;
 }
 
-int bh_ray_pipeline_pass(bh_ray_pipeline *p, const bh_camera_uniform *camera, const bh_black_hole_uniform *black_hole,
-                         const bh_ray_details *details, void *cuda_stream)
+static int build_pass_params(bh_ray_pipeline *p, const bh_camera_uniform *camera, const bh_black_hole_uniform *black_hole,
+                             const bh_ray_details *details, const char *who, PassParams &P)
 {
-    if (!p || !camera || !black_hole || !details) { set_error("bh_ray_pipeline_pass: NULL argument"); return BH_ERR_INVALID; }
+    if (!p || !camera || !black_hole || !details) { set_error("%s: NULL argument", who); return BH_ERR_INVALID; }
     bh_ctx *c = p->ctx;
-    if (!c->tex[0] || !c->tex[1] || !c->tex[2]) { set_error("bh_ray_pipeline_pass: textures not set (bh_ctx_set_texture for COLOR, DISK and SKY)"); return BH_ERR_STATE; }
+    if (!c->tex[0] || !c->tex[1] || !c->tex[2]) { set_error("%s: textures not set (bh_ctx_set_texture for COLOR, DISK and SKY)", who); return BH_ERR_STATE; }
     if (details->model_count < 0 || details->model_count > c->models_uploaded) {
-        set_error("bh_ray_pipeline_pass: model_count=%d but %d model(s) uploaded", details->model_count, c->models_uploaded);
+        set_error("%s: model_count=%d but %d model(s) uploaded", who, details->model_count, c->models_uploaded);
         return BH_ERR_INVALID;
     }
-    if (details->integration_method != 0 && details->integration_method != 1) {
-        // ray.wgsl:525: anything non-zero takes the RK branch
-    }
-    BH_CUDA(cudaSetDevice(c->device));
-    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
-    PassParams P;
     memset(&P, 0, sizeof P);
     P.cam = *camera; P.hole = *black_hole; P.det = *details;
-    if (P.det.integration_method != 0) P.det.integration_method = 1;
+    if (P.det.integration_method != 0) P.det.integration_method = 1;        // ray.wgsl:525: anything non-zero takes the RK branch
     P.color = DevTexture{ c->tex[0], c->tex_w[0], c->tex_h[0] };
     P.disk = DevTexture{ c->tex[1], c->tex_w[1], c->tex_h[1] };
     P.sky = DevTexture{ c->tex[2], c->tex_w[2], c->tex_h[2] };
@@ -324,11 +328,86 @@ int bh_ray_pipeline_pass(bh_ray_pipeline *p, const bh_camera_uniform *camera, co
     P.aux_hit = p->aux_hit; P.aux_steps = p->aux_steps; P.aux_class = p->aux_class;
     P.stats = p->stats; P.work = p->work; P.queue = p->queue;
     P.tiles_x = (int)((p->w + 7) / 8);
+    P.item_begin = 0;
     P.n_items = (unsigned)P.tiles_x * (unsigned)((p->local_rows + 3) / 4);
+    return BH_OK;
+}
+
+int bh_ray_pipeline_pass(bh_ray_pipeline *p, const bh_camera_uniform *camera, const bh_black_hole_uniform *black_hole,
+                         const bh_ray_details *details, void *cuda_stream)
+{
+    PassParams P;
+    const int rc = build_pass_params(p, camera, black_hole, details, "bh_ray_pipeline_pass", P);
+    if (rc != BH_OK) return rc;
+    bh_ctx *c = p->ctx;
+    BH_CUDA(cudaSetDevice(c->device));
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
     LaunchConfig cfg{ c->sm_count, c->numeric_mode };
     p->last_stream = stream; p->ran = true;
     if (p->local_rows == 0) return BH_OK;
     BH_CUDA(launch_ray_pass(P, cfg, stream));
+    return BH_OK;
+}
+
+int bh_ray_pipeline_pass_to_host(bh_ray_pipeline *p, const bh_camera_uniform *camera, const bh_black_hole_uniform *black_hole,
+                                 const bh_ray_details *details, float *pinned_host_rgba32f, uint32_t n_chunks, void *cuda_stream)
+{
+    PassParams P;
+    const int rc = build_pass_params(p, camera, black_hole, details, "bh_ray_pipeline_pass_to_host", P);
+    if (rc != BH_OK) return rc;
+    if (!pinned_host_rgba32f) { set_error("bh_ray_pipeline_pass_to_host: host buffer is NULL"); return BH_ERR_INVALID; }
+    if (n_chunks == 0) n_chunks = 1;
+    if (n_chunks > 16) n_chunks = 16;
+    bh_ctx *c = p->ctx;
+    BH_CUDA(cudaSetDevice(c->device));
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    if (!p->copy_stream) {
+        BH_CUDA(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+        for (auto &e : p->chunk_done) BH_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        BH_CUDA(cudaEventCreateWithFlags(&p->copy_done, cudaEventDisableTiming));
+    }
+    LaunchConfig cfg{ c->sm_count, c->numeric_mode };
+    p->last_stream = stream; p->ran = true;
+    if (p->local_rows == 0) return BH_OK;
+    const size_t row_bytes = (size_t)p->w * sizeof(float4);
+    if (P.prev != nullptr) n_chunks = 1;                 // fine levels: classification + queue cover the whole level at once
+    if (n_chunks == 1) {
+        BH_CUDA(launch_ray_pass(P, cfg, stream));
+        BH_CUDA(cudaEventRecord(p->chunk_done[0], stream));
+        BH_CUDA(cudaStreamWaitEvent(p->copy_stream, p->chunk_done[0], 0));
+        BH_CUDA(cudaMemcpyAsync(pinned_host_rgba32f, p->out(), row_bytes * p->local_rows, cudaMemcpyDeviceToHost, p->copy_stream));
+    } else {
+        // base level: tiles are ordered row-major, so a tile-row range is a contiguous band of output rows.  Each band is a
+        // separate launch; its D2H copy runs on the copy stream while the next band is traced.
+        const unsigned tile_rows = (p->local_rows + 3) / 4;
+        for (uint32_t k = 0; k < n_chunks; ++k) {
+            const unsigned tr0 = (unsigned)((uint64_t)tile_rows * k / n_chunks), tr1 = (unsigned)((uint64_t)tile_rows * (k + 1) / n_chunks);
+            if (tr1 == tr0) continue;
+            PassParams Q = P;
+            Q.item_begin = tr0 * (unsigned)P.tiles_x;
+            Q.n_items = tr1 * (unsigned)P.tiles_x;
+            BH_CUDA(launch_trace_range(Q, cfg, k == 0, stream));
+            BH_CUDA(cudaEventRecord(p->chunk_done[k], stream));
+            BH_CUDA(cudaStreamWaitEvent(p->copy_stream, p->chunk_done[k], 0));
+            const size_t r0 = (size_t)tr0 * 4, r1 = (size_t)tr1 * 4 < p->local_rows ? (size_t)tr1 * 4 : p->local_rows;
+            BH_CUDA(cudaMemcpyAsync(reinterpret_cast<char *>(pinned_host_rgba32f) + r0 * row_bytes,
+                                    reinterpret_cast<const char *>(p->out()) + r0 * row_bytes, (r1 - r0) * row_bytes,
+                                    cudaMemcpyDeviceToHost, p->copy_stream));
+        }
+    }
+    BH_CUDA(cudaEventRecord(p->copy_done, p->copy_stream));
+    BH_CUDA(cudaStreamWaitEvent(stream, p->copy_done, 0));          // work enqueued later on `stream` sees the copy finished
+    p->copy_pending = true;
+    return BH_OK;
+}
+
+int bh_ray_pipeline_sync(bh_ray_pipeline *p)
+{
+    if (!p) { set_error("bh_ray_pipeline_sync: NULL pipeline"); return BH_ERR_INVALID; }
+    if (!p->ran) return BH_OK;
+    BH_CUDA(cudaSetDevice(p->ctx->device));
+    BH_CUDA(cudaStreamSynchronize(p->last_stream));
+    if (p->copy_pending) { BH_CUDA(cudaStreamSynchronize(p->copy_stream)); p->copy_pending = false; }
     return BH_OK;
 }
 

@@ -48,7 +48,8 @@ struct PassParams {
     unsigned long long *stats;       // kStatCount
     unsigned int *work;              // kWorkCount
     unsigned int *queue;             // local pixel indices awaiting a trace (fine levels)
-    unsigned int n_items;            // tile mode: number of 8x4 warp tiles
+    unsigned int n_items;            // tile mode: items [item_begin, n_items) are 8x4 warp tiles of this launch
+    unsigned int item_begin;
     int tiles_x;
 };
 
@@ -68,6 +69,8 @@ struct LaunchConfig {
 
 // launchers (ray_kernels.cu)
 cudaError_t launch_ray_pass(const PassParams &p, const LaunchConfig &cfg, cudaStream_t stream);
+// base level only: trace the tile range [p.item_begin, p.n_items) without resetting the pass statistics
+cudaError_t launch_trace_range(const PassParams &p, const LaunchConfig &cfg, bool reset_stats, cudaStream_t stream);
 cudaError_t launch_sky_pass(const SkyParams &p, const LaunchConfig &cfg, cudaStream_t stream);
 cudaError_t launch_math_probe(int fn, const float *a, const float *b, float *out, size_t n, cudaStream_t stream);
 

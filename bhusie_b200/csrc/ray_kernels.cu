@@ -22,6 +22,42 @@
 
 namespace bh {
 
+// ------------------------------------------------------------------------------------------------
+// TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers: global -> shared staging of the BVH top
+// ------------------------------------------------------------------------------------------------
+namespace tma {
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+}  // namespace tma
+
+// BVH top staged per CTA: ModelUniform header (position, visible, ...: 48 B) + the first kTopNodes nodes in the
+// reference's pre-order numbering (root, its two children, the left spine ...).  A ray that misses the mesh — the
+// common case — touches only nodes 0,1,2, so its whole flat-space test runs out of shared memory.
+constexpr int kTopNodes = 256;
+constexpr int kTopHeaderBytes = 64;                       // 48 used, padded to keep the nodes 16-byte aligned
+constexpr int kTopBytes = kTopHeaderBytes + kTopNodes * 32;
+
 #define BH_NUM_NS lit
 #define BH_FUSED 0
 #include "ray_impl.cuh"
@@ -67,7 +103,7 @@ static cudaError_t launch_trace(K kernel, bool queue, const PassParams &p, const
     if (per_sm < 1) per_sm = 1;
     unsigned grid = (unsigned)(cfg.sm_count * per_sm);      // persistent: one wave of resident CTAs
     if (!queue) {
-        const unsigned need = (p.n_items + 3u) / 4u;
+        const unsigned need = (p.n_items - p.item_begin + 3u) / 4u;
         if (need < grid) grid = need ? need : 1u;
     }
     kernel<<<grid, 128, 0, stream>>>(p);
@@ -102,6 +138,18 @@ cudaError_t launch_ray_pass(const PassParams &p, const LaunchConfig &cfg, cudaSt
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     return launch_trace_mode<true>(p, cfg, stream);
+}
+
+cudaError_t launch_trace_range(const PassParams &p, const LaunchConfig &cfg, bool reset_stats, cudaStream_t stream)
+{
+    cudaError_t e = cudaMemsetAsync(p.work, 0, sizeof(unsigned) * kWorkCount, stream);
+    if (e != cudaSuccess) return e;
+    if (reset_stats) {
+        e = cudaMemsetAsync(p.stats, 0, sizeof(unsigned long long) * kStatCount, stream);
+        if (e != cudaSuccess) return e;
+    }
+    if (p.item_begin >= p.n_items) return cudaSuccess;
+    return launch_trace_mode<false>(p, cfg, stream);
 }
 
 cudaError_t launch_sky_pass(const SkyParams &s, const LaunchConfig &cfg, cudaStream_t stream)

@@ -165,6 +165,16 @@ class RayPipeline:
         det = _bytes(details, RAY_DETAILS_SIZE)
         _lib.check(self._lib.bh_ray_pipeline_pass(self._h, cam, hole, det, _stream_ptr(stream)))
 
+    def pass_to_host(self, camera, black_hole, details, host_ptr: int, n_chunks: int = 8, stream=None):
+        """pass_() followed by a chunk-overlapped copy of the RGBA32F output into pinned host memory (async)."""
+        cam = _bytes(camera, CAMERA_UNIFORM_SIZE)
+        hole = _bytes(black_hole, BLACK_HOLE_UNIFORM_SIZE)
+        det = _bytes(details, RAY_DETAILS_SIZE)
+        _lib.check(self._lib.bh_ray_pipeline_pass_to_host(self._h, cam, hole, det, C.c_void_p(host_ptr), n_chunks, _stream_ptr(stream)))
+
+    def sync(self):
+        _lib.check(self._lib.bh_ray_pipeline_sync(self._h))
+
     def read(self, aux: bool = True) -> dict:
         rows, w = self.local_rows, self.width
         out = {"rgba": np.empty((rows, w, 4), np.float32)}

@@ -149,6 +149,15 @@ int  bh_ray_pipeline_pass(bh_ray_pipeline *p, const bh_camera_uniform *camera,
                           const bh_black_hole_uniform *black_hole, const bh_ray_details *details,
                           void *cuda_stream);
 
+/* pass + read-back in one call for callers whose consumer lives on the host side of the bus (the reference's wgpu
+ * post chain): same as bh_ray_pipeline_pass, then the RGBA32F output is copied to `pinned_host_rgba32f`
+ * (local_rows*width*16 B of page-locked memory).  On the base level the frame is traced as n_chunks (1..16) row bands and
+ * each band's D2H copy overlaps the tracing of the next.  Asynchronous; bh_ray_pipeline_sync() waits for kernels and copies. */
+int  bh_ray_pipeline_pass_to_host(bh_ray_pipeline *p, const bh_camera_uniform *camera,
+                                  const bh_black_hole_uniform *black_hole, const bh_ray_details *details,
+                                  float *pinned_host_rgba32f, uint32_t n_chunks, void *cuda_stream);
+int  bh_ray_pipeline_sync(bh_ray_pipeline *p);
+
 /* RayPipeline::output_view: device pointer, row-major RGBA32F, pitch = width*16 B, local_rows rows.
  * alpha==1: finished colour; alpha==0: rgb is the escaped-ray direction (ray.wgsl:592-595). */
 const float *bh_ray_pipeline_output(const bh_ray_pipeline *p);

@@ -315,6 +315,31 @@ def test_bind_output_and_streams(ctx_small):
     rp.close()
 
 
+def test_pass_to_host_chunked(ctx_small):
+    """bh_ray_pipeline_pass_to_host: chunk-overlapped read-back gives the same bytes and statistics as pass + read."""
+    import torch
+    cam, hole, det = U.Camera(), U.BlackHole(), U.RayDetails(integration_method=1, model_count=1)
+    for (w, h, chunks) in ((120, 67, 8), (64, 9, 16), (33, 40, 3), (16, 4, 5)):
+        rp, ref, st = render(ctx_small, w, h, cam, hole, det, aux=0)
+        host = torch.zeros((h, w, 4), dtype=torch.float32).pin_memory()
+        rp.pass_to_host(cam, hole, det, host.data_ptr(), chunks)
+        rp.sync()
+        assert np.array_equal(bits(host.numpy()), bits(ref["rgba"])), (w, h, chunks)
+        assert rp.stats(strict=False) == st
+        rp.close()
+    # fine level: falls back to one chunk
+    l0 = P.RayPipeline(ctx_small, 32, 18)
+    l0.pass_(cam, hole, det)
+    l1 = P.RayPipeline(ctx_small, 94, 52, l0)
+    l1.pass_(cam, hole, det)
+    ref = l1.read()["rgba"]
+    host = torch.zeros((52, 94, 4), dtype=torch.float32).pin_memory()
+    l1.pass_to_host(cam, hole, det, host.data_ptr(), 8)
+    l1.sync()
+    assert np.array_equal(bits(host.numpy()), bits(ref))
+    l1.close(); l0.close()
+
+
 def test_error_codes(small_scene):
     tex, blob, _ = small_scene
     lib = _lib.load()
