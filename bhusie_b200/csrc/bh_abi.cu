@@ -380,13 +380,15 @@ int bh_ray_pipeline_pass_to_host(bh_ray_pipeline *p, const bh_camera_uniform *ca
         // base level: tiles are ordered row-major, so a tile-row range is a contiguous band of output rows.  Each band is a
         // separate launch; its D2H copy runs on the copy stream while the next band is traced.
         const unsigned tile_rows = (p->local_rows + 3) / 4;
+        bool first = true;
         for (uint32_t k = 0; k < n_chunks; ++k) {
             const unsigned tr0 = (unsigned)((uint64_t)tile_rows * k / n_chunks), tr1 = (unsigned)((uint64_t)tile_rows * (k + 1) / n_chunks);
             if (tr1 == tr0) continue;
             PassParams Q = P;
             Q.item_begin = tr0 * (unsigned)P.tiles_x;
             Q.n_items = tr1 * (unsigned)P.tiles_x;
-            BH_CUDA(launch_trace_range(Q, cfg, k == 0, stream));
+            BH_CUDA(launch_trace_range(Q, cfg, first, stream));
+            first = false;
             BH_CUDA(cudaEventRecord(p->chunk_done[k], stream));
             BH_CUDA(cudaStreamWaitEvent(p->copy_stream, p->chunk_done[k], 0));
             const size_t r0 = (size_t)tr0 * 4, r1 = (size_t)tr1 * 4 < p->local_rows ? (size_t)tr1 * 4 : p->local_rows;
