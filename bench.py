@@ -192,7 +192,7 @@ def run_ours(args):
     cam, hole = U.Camera(), U.BlackHole()
     det = U.RayDetails(integration_method=1, model_count=1)
 
-    frame = TiledFrame(ctx, W, H, rank, world, band_rows=args.band_rows)
+    frame = TiledFrame(ctx, W, H, rank, world, band_rows=args.band_rows, exchange=args.exchange)
     stream = torch.cuda.current_stream()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
@@ -255,6 +255,7 @@ def run_ours(args):
             frame.render(cam, hole, det, stream)
             if rank == 0:
                 host_frame.copy_(frame.frame_tensor(), non_blocking=True)
+            frame.consumed(stream)
             stream.synchronize()
 
     for _ in range(max(1, min(args.warmup, 2))):
@@ -297,6 +298,8 @@ def run_ours(args):
             "config": {"workload": WORKLOAD if (W, H) == (3840, 2160) else f"{W}x{H} variant of: {WORKLOAD}", "width": W, "height": H,
                        "integrator": "cash-karp-rk", "step_size": 0.15, "max_iterations": 2000, "triangles": mesh_info.get("triangle_count"),
                        "bvh_nodes": mesh_info.get("nodes_used"), "tiling": f"cyclic bands of {frame.band_rows} rows over {world} rank(s)",
+                       "exchange": {"p2p": "ray kernel stores finished pixels directly into rank 0's frame over NVLink (CUDA IPC peer memory) + one 4-byte all-reduce",
+                                    "nccl": "NCCL gather of compact band buffers to rank 0 + de-interleave copy", "none": "single GPU"}[frame.exchange],
                        "l2_flush": "256 MiB memset before every step, inside the timed region",
                        "ray_steps_per_frame": total["ray_steps"],
                        "numerics": ("FUSED: explicit fma contraction + reciprocal-multiply, det-math transcendentals (bit-exact vs oracle 'fused')"
@@ -306,7 +309,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(W * H * 16), "ms_per_step": 1000.0 * e2e_s / args.steps, "fps": args.steps / e2e_s,
                     "frame_checksum": checksum,
                     "path": (f"bh_ctx_upload_models_async + bh_ray_pipeline_pass_to_host({args.e2e_chunks} bands, D2H overlapped) + sync"
-                             if world == 1 else "upload_models_async + tiled pass + NCCL gather + D2H of the assembled frame")},
+                             if world == 1 else f"upload_models_async + tiled pass ({frame.exchange} exchange) + D2H of the assembled frame")},
             "gpu_launches": int(args.steps * 1),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
@@ -329,6 +332,7 @@ def run_ours(args):
             except Exception as ex:   # the oracle is a checker; its absence must not hide the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"unavailable: {ex}"}
         print(json.dumps(line))
+    frame.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -345,6 +349,8 @@ def main():
     ap.add_argument("--band-rows", type=int, default=8)
     ap.add_argument("--numeric-mode", default="fused", choices=["fused", "literal"])
     ap.add_argument("--e2e-chunks", type=int, default=8)
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: p2p = kernels store straight into rank 0's frame over NVLink (CUDA IPC); nccl = gather of band buffers")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--allow-short-warmup", action="store_true", help="profiling runs only (ncu); numbers from such runs are not bench values")
     args = ap.parse_args()

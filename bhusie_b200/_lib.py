@@ -50,6 +50,10 @@ SYMBOLS = {
     "bh_ray_pipeline_local_rows": (_U32, [_VP]),
     "bh_ray_pipeline_enable_aux": (C.c_int, [_VP, _U32]),
     "bh_ray_pipeline_bind_output": (C.c_int, [_VP, _VP]),
+    "bh_ray_pipeline_bind_frame": (C.c_int, [_VP, _VP]),
+    "bh_shared_frame_create": (C.c_int, [_VP, C.c_size_t, C.POINTER(_VP), _VP]),
+    "bh_shared_frame_open": (C.c_int, [_VP, _VP, C.POINTER(_VP)]),
+    "bh_shared_frame_release": (C.c_int, [_VP, _VP, C.c_int]),
     "bh_ray_pipeline_pass": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
     "bh_ray_pipeline_pass_to_host": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _U32, _VP]),
     "bh_ray_pipeline_sync": (C.c_int, [_VP]),

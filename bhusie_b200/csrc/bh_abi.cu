@@ -64,6 +64,7 @@ struct bh_ray_pipeline {
     float4 *own_out = nullptr;
     size_t own_out_rows = 0;
     float4 *bound_out = nullptr;
+    float4 *bound_frame = nullptr;                   // full-frame target (global row addressing), local or peer memory
     int32_t *aux_hit = nullptr;
     uint32_t *aux_steps = nullptr;
     uint8_t *aux_class = nullptr;
@@ -77,7 +78,7 @@ struct bh_ray_pipeline {
     cudaEvent_t chunk_done[16] = {};
     cudaEvent_t copy_done = nullptr;
     bool copy_pending = false;
-    float4 *out() const { return bound_out ? bound_out : own_out; }
+    float4 *out() const { return bound_frame ? bound_frame : (bound_out ? bound_out : own_out); }
 };
 
 struct bh_sky_pipeline {
@@ -321,6 +322,7 @@ static int build_pass_params(bh_ray_pipeline *p, const bh_camera_uniform *camera
     P.sky = DevTexture{ c->tex[2], c->tex_w[2], c->tex_h[2] };
     P.models = c->models;
     P.out = p->out();
+    P.out_global_rows = p->bound_frame ? 1 : 0;
     P.prev = p->prev ? p->prev->out() : nullptr;
     P.w = (int)p->w; P.h = (int)p->h;
     P.pw = p->prev ? (int)p->prev->w : 1; P.ph = p->prev ? (int)p->prev->h : 1;
@@ -330,6 +332,48 @@ static int build_pass_params(bh_ray_pipeline *p, const bh_camera_uniform *camera
     P.tiles_x = (int)((p->w + 7) / 8);
     P.item_begin = 0;
     P.n_items = (unsigned)P.tiles_x * (unsigned)((p->local_rows + 3) / 4);
+    return BH_OK;
+}
+
+int bh_ray_pipeline_bind_frame(bh_ray_pipeline *p, void *device_frame_rgba32f)
+{
+    if (!p || ((uintptr_t)device_frame_rgba32f & 15u)) { set_error("bh_ray_pipeline_bind_frame: pointer must be 16-byte aligned"); return BH_ERR_INVALID; }
+    p->bound_frame = static_cast<float4 *>(device_frame_rgba32f);
+    return BH_OK;
+}
+
+// ---- frames shared between the processes of one node (CUDA IPC): rank 0 owns, the others map it over NVLink
+int bh_shared_frame_create(bh_ctx *ctx, size_t nbytes, void **device_ptr, uint8_t handle_out[64])
+{
+    if (!ctx || !device_ptr || !handle_out || nbytes == 0) { set_error("bh_shared_frame_create: bad argument"); return BH_ERR_INVALID; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    BH_CUDA(cudaSetDevice(ctx->device));
+    void *ptr = nullptr;
+    BH_CUDA(cudaMalloc(&ptr, nbytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, ptr);
+    if (e != cudaSuccess) { cudaFree(ptr); return cuda_fail(e, "cudaIpcGetMemHandle"); }
+    memcpy(handle_out, &h, 64);
+    *device_ptr = ptr;
+    return BH_OK;
+}
+
+int bh_shared_frame_open(bh_ctx *ctx, const uint8_t handle[64], void **device_ptr)
+{
+    if (!ctx || !handle || !device_ptr) { set_error("bh_shared_frame_open: bad argument"); return BH_ERR_INVALID; }
+    BH_CUDA(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    BH_CUDA(cudaIpcOpenMemHandle(device_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return BH_OK;
+}
+
+int bh_shared_frame_release(bh_ctx *ctx, void *device_ptr, int owner)
+{
+    if (!ctx || !device_ptr) { set_error("bh_shared_frame_release: bad argument"); return BH_ERR_INVALID; }
+    BH_CUDA(cudaSetDevice(ctx->device));
+    if (owner) BH_CUDA(cudaFree(device_ptr));
+    else BH_CUDA(cudaIpcCloseMemHandle(device_ptr));
     return BH_OK;
 }
 
@@ -423,6 +467,7 @@ int bh_ray_pipeline_read(bh_ray_pipeline *p, float *host_rgba32f, int32_t *host_
         set_error("bh_ray_pipeline_read: aux buffer requested but not enabled (bh_ray_pipeline_enable_aux)");
         return BH_ERR_STATE;
     }
+    if (host_rgba32f && p->bound_frame) { set_error("bh_ray_pipeline_read: output is bound to an external frame (bh_ray_pipeline_bind_frame); read the frame instead"); return BH_ERR_STATE; }
     BH_CUDA(cudaSetDevice(p->ctx->device));
     BH_CUDA(cudaStreamSynchronize(p->last_stream));
     const size_t px = (size_t)p->local_rows * p->w;

@@ -38,7 +38,8 @@ struct PassParams {
     bh_ray_details det;
     DevTexture color, disk, sky;
     const unsigned char *models;     // kModelStride per model
-    float4 *out;                     // local_rows x w
+    float4 *out;                     // local_rows x w (band-major), or the whole h x w frame when out_global_rows != 0
+    int out_global_rows;             // write row gy of a full frame (possibly a peer GPU's, over NVLink) instead of local row ly
     const float4 *prev;              // ph x pw (nullptr: base level)
     int w, h, pw, ph;
     int band_rows, rank, n_ranks, local_rows;

@@ -6,6 +6,15 @@ the cost that concentrates around the hole, the disk and the mesh.  Every rank h
 scene (textures + ModelUniform), renders its bands into a compact band-major buffer, and rank 0
 receives all of them with ONE gather (NCCL over NVLink) and de-interleaves them into the frame.
 There is no other collective on the data path.
+
+Two exchanges are implemented:
+  "nccl"  every rank renders into a compact band buffer; rank 0 gathers them (NCCL send/recv over NVLink) and
+          de-interleaves with one copy.  The plain-library baseline.
+  "p2p"   (default when CUDA IPC is available) rank 0 owns the frame and exports it with CUDA IPC; every other rank
+          maps it and its ray kernel stores finished pixels STRAIGHT into rank 0's memory at their global row
+          (bh_ray_pipeline_bind_frame) — 16-byte stores over NVLink while the warp keeps tracing, so the exchange is
+          fused into the pass and overlaps it completely.  One 4-byte all-reduce per frame orders "all ranks done"
+          before rank 0 consumes the frame.
 """
 from __future__ import annotations
 
@@ -71,14 +80,26 @@ def gather_bands(local, layout: BandLayout, rank: int, frame=None, staging=None,
     return None
 
 
-class TiledFrame:
-    """One frame of the single-level ray pass on `world` ranks: RayPipeline with cyclic-band tiling
-    rendering straight into a torch tensor (bh_ray_pipeline_bind_output), then gather_bands()."""
+class _DevicePointer:
+    """Minimal __cuda_array_interface__ carrier so torch can view memory the library allocated."""
 
-    def __init__(self, ctx, width: int, height: int, rank: int = 0, world: int = 1, band_rows: int = 8, aux: int = 0):
+    def __init__(self, ptr: int, shape: tuple):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (ptr, False), "version": 2, "strides": None}
+
+
+class TiledFrame:
+    """One frame of the single-level ray pass on `world` ranks: RayPipeline with cyclic-band tiling, exchanged
+    either by NCCL gather ("nccl") or by direct peer stores into rank 0's frame ("p2p")."""
+
+    def __init__(self, ctx, width: int, height: int, rank: int = 0, world: int = 1, band_rows: int = 8, aux: int = 0,
+                 exchange: str = "p2p"):
         import torch
         from .pipelines import RayPipeline
 
+        if exchange not in ("p2p", "nccl"):
+            raise ValueError("exchange must be 'p2p' or 'nccl'")
+        self.ctx = ctx
+        self.exchange = exchange if world > 1 else "none"
         self.rank, self.world, self.width, self.height = rank, world, width, height
         self.band_rows = band_rows if world > 1 else height
         self.layout = BandLayout(height, self.band_rows, world)
@@ -87,9 +108,26 @@ class TiledFrame:
             self.pipeline.set_tiling(self.band_rows, rank, world)
         assert self.pipeline.local_rows == self.layout.local_rows(rank)
         dev = torch.device("cuda", ctx.device)
+        self.frame = self.staging = self.row_index = self.local = None
+        self._shared_ptr = 0
+        if self.exchange == "p2p":
+            import torch.distributed as dist
+            nbytes = height * width * 16
+            if rank == 0:
+                self._shared_ptr, handle = ctx.shared_frame_create(nbytes)
+                h = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+            else:
+                h = torch.empty(64, dtype=torch.uint8, device=dev)
+            dist.broadcast(h, 0)
+            if rank != 0:
+                self._shared_ptr = ctx.shared_frame_open(bytes(h.cpu().tolist()))
+            self.pipeline.bind_frame(self._shared_ptr)
+            self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
+            if rank == 0:
+                self.frame = torch.as_tensor(_DevicePointer(self._shared_ptr, (height, width, 4)), device=dev)
+            return
         self.local = torch.zeros((self.layout.max_local_rows, width, 4), dtype=torch.float32, device=dev)
         self.pipeline.bind_output(self.local.data_ptr())
-        self.frame = self.staging = self.row_index = None
         if rank == 0 and world > 1:
             self.frame = torch.zeros((height, width, 4), dtype=torch.float32, device=dev)
             self.staging = torch.empty((world,) + tuple(self.local.shape), dtype=torch.float32, device=dev)
@@ -100,8 +138,28 @@ class TiledFrame:
         self.pipeline.pass_(camera, black_hole, details, stream)
 
     def gather(self, stream=None):
-        if self.world > 1:
+        """After this (stream-ordered) rank 0's frame holds every rank's rows."""
+        if self.exchange == "p2p":
+            import torch.distributed as dist
+            dist.all_reduce(self._flag)          # 4 bytes: completes on a rank only after every rank's kernel has finished
+        elif self.world > 1:
             gather_bands(self.local, self.layout, self.rank, self.frame, self.staging, self.row_index)
+
+    def consumed(self, stream=None):
+        """Call (on every rank) after rank 0 has finished reading the frame and before the next render: in p2p mode the
+        other ranks write into rank 0's memory, so they must not start the next frame while it is still being read."""
+        if self.exchange == "p2p":
+            import torch.distributed as dist
+            dist.all_reduce(self._flag)
+
+    def close(self):
+        self.pipeline.bind_frame(None)
+        if self._shared_ptr:
+            import torch
+            torch.cuda.synchronize()
+            self.frame = None
+            self.ctx.shared_frame_release(self._shared_ptr, owner=self.rank == 0)
+            self._shared_ptr = 0
 
     def render(self, camera, black_hole, details, stream=None):
         self.render_local(camera, black_hole, details, stream)

@@ -102,6 +102,22 @@ class Context:
         pos = (C.c_float * 3)(*map(float, position))
         _lib.check(self._lib.bh_ctx_set_model_header(self._h, index, pos, int(visible)))
 
+    def shared_frame_create(self, nbytes: int) -> tuple[int, bytes]:
+        """cudaMalloc + cudaIpcGetMemHandle: (device pointer, 64-byte handle) for bind_frame on other ranks."""
+        ptr = C.c_void_p()
+        handle = (C.c_uint8 * 64)()
+        _lib.check(self._lib.bh_shared_frame_create(self._h, nbytes, C.byref(ptr), handle))
+        return int(ptr.value), bytes(handle)
+
+    def shared_frame_open(self, handle: bytes) -> int:
+        ptr = C.c_void_p()
+        buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+        _lib.check(self._lib.bh_shared_frame_open(self._h, buf, C.byref(ptr)))
+        return int(ptr.value)
+
+    def shared_frame_release(self, ptr: int, owner: bool):
+        _lib.check(self._lib.bh_shared_frame_release(self._h, C.c_void_p(ptr), 1 if owner else 0))
+
     def math_probe(self, fn: str, a: np.ndarray, b: np.ndarray | None = None) -> np.ndarray:
         codes = {"pow": 0, "pow5": 1, "pow4": 2, "sin": 3, "cos": 4, "tan": 5, "atan2": 6, "acos": 7}
         a = np.ascontiguousarray(a, dtype=np.float32)
@@ -152,6 +168,10 @@ class RayPipeline:
 
     def bind_output(self, device_ptr: int | None):
         _lib.check(self._lib.bh_ray_pipeline_bind_output(self._h, C.c_void_p(device_ptr or 0)))
+
+    def bind_frame(self, device_ptr: int | None):
+        """Write rows at their GLOBAL index into a full frame (local or peer-mapped) instead of the compact local buffer."""
+        _lib.check(self._lib.bh_ray_pipeline_bind_frame(self._h, C.c_void_p(device_ptr or 0)))
 
     @property
     def output_ptr(self) -> int:

@@ -142,6 +142,17 @@ int  bh_ray_pipeline_enable_aux(bh_ray_pipeline *p, uint32_t aux_mask);
  * pipeline's own buffer — lets the host hand in a torch tensor / NCCL send buffer.  NULL restores. */
 int  bh_ray_pipeline_bind_output(bh_ray_pipeline *p, void *device_rgba32f);
 
+/* Multi-GPU without a gather step: render this pipeline's rows directly into a FULL width x height RGBA32F frame at
+ * their global row index.  The frame may be local, or another GPU's memory mapped through bh_shared_frame_open — the
+ * kernel's 16-byte stores then travel over NVLink while it is still tracing, so the "collective" is fused into the
+ * pass.  NULL restores the compact local buffer.  (With a frame bound, bh_ray_pipeline_read cannot return RGBA.) */
+int  bh_ray_pipeline_bind_frame(bh_ray_pipeline *p, void *device_frame_rgba32f);
+/* CUDA-IPC plumbing for that frame: the owner allocates and exports a 64-byte handle (sent to the other processes of
+ * the node by any means, e.g. a torch.distributed broadcast); the others map it; both release it when done. */
+int  bh_shared_frame_create(bh_ctx *ctx, size_t nbytes, void **device_ptr, uint8_t handle_out[64]);
+int  bh_shared_frame_open(bh_ctx *ctx, const uint8_t handle[64], void **device_ptr);
+int  bh_shared_frame_release(bh_ctx *ctx, void *device_ptr, int owner);
+
 /* RayPipeline::pass: enqueue the pass on `cuda_stream` (a cudaStream_t; NULL = default stream) and
  * return — same contract as recording into a ComputePass.  The three pointers are HOST bytes, read
  * before return. */
