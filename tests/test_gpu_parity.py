@@ -164,6 +164,44 @@ def test_parameter_variants_bit_exact(ctx_small, oracle, small_oracle_scene, var
             ctx_small.set_model_header(0, (-10.0, 0.0, 30.0), 1)
 
 
+def test_random_scenes_bit_exact(ctx_small, oracle, small_oracle_scene):
+    """Seeded fuzz over the uniform space the UI exposes (ui/render_settings.rs:62-66,164; black_hole_settings.rs:41-58;
+    camera_settings.rs:36-43): camera pose, fov, disk geometry/orientation, relativity radius, feather, step size,
+    integrator, time, model placement.  Every frame must match the oracle bit for bit, including the counters."""
+    rng = np.random.default_rng(20261017)
+    blob0 = small_oracle_scene.models
+    n_hit = 0
+    for case in range(24):
+        pos = rng.normal(size=3) * np.array([12.0, 6.0, 14.0]) + np.array([0.0, 0.0, -18.0])
+        if np.linalg.norm(pos) < 3.0:
+            pos = pos / np.linalg.norm(pos) * 6.0
+        fwd = -pos / np.linalg.norm(pos) + rng.normal(size=3) * 0.15          # roughly towards the hole, not normalised (Q21)
+        cam = U.Camera(position=tuple(pos), forward=tuple(fwd), fov=float(rng.uniform(0.5, 1.6)))
+        inner = float(rng.uniform(2.0, 4.0))
+        hole = U.BlackHole(accretion_disk_rotation=tuple(rng.uniform(-1.5, 1.5, 3)), accretion_disk_inner=inner,
+                           accretion_disk_outer=float(inner + rng.uniform(2.0, 12.0)), rotation_speed=float(rng.uniform(-2, 2)),
+                           relativity_sphere_radius=float(rng.uniform(12.0, 40.0)), show_disk_texture=int(rng.integers(0, 2)),
+                           show_red_shift=int(rng.integers(0, 2)), feather_amount=float(rng.uniform(0.05, 1.0)))
+        det = U.RayDetails(integration_method=int(rng.integers(0, 2)), model_count=1, time=float(rng.uniform(0, 50)),
+                           step_size=float(rng.uniform(0.05, 0.6)), max_iterations=int(rng.integers(50, 1500)))
+        mpos = tuple(rng.normal(size=3) * 8 + np.array([-6.0, 0.0, 18.0]))
+        ctx_small.set_model_header(0, mpos, 1)
+        blob = blob0.copy()
+        blob[0:12].view(np.float32)[:] = mpos
+        osc = oracle.OracleScene(small_oracle_scene.color, small_oracle_scene.disk, small_oracle_scene.sky, blob)
+        w, h = int(rng.integers(17, 72)), int(rng.integers(9, 40))
+        try:
+            rp, dev, st = render(ctx_small, w, h, cam, hole, det)
+            ora = oracle.ray_pass(osc, w, h, cam.uniform(), hole.uniform(), det.uniform(), flavour=fl(ctx_small))
+            assert_bit_exact(dev, ora, f"fuzz case {case}")
+            assert_stats(st, ora.counters)
+            n_hit += int((dev["hit"] >= 0).sum())
+            rp.close()
+        finally:
+            ctx_small.set_model_header(0, (-10.0, 0.0, 30.0), 1)
+    assert n_hit > 0
+
+
 def test_ragged_sizes_bit_exact(ctx_small, oracle, small_oracle_scene):
     """Frame sizes that are not multiples of the 8x4 warp tile, down to the 2x2 minimum."""
     cam, hole, det = U.Camera(), U.BlackHole(), U.RayDetails(integration_method=1, model_count=1)
