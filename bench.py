@@ -281,12 +281,15 @@ def run_ours(args):
         abytes = algorithmic_bytes(local, n_px_local)
         achieved = abytes / (kernel_ms * 1e-3) / 1e9
         traffic = None
+        inst_per_step = None
         # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel on this workload
         prof = os.path.join(ROOT, "profiles", "trace_kernel_dram.json")
         if os.path.exists(prof) and (W, H) == (3840, 2160) and world == 1:
             try:
                 with open(prof) as f:
-                    traffic = json.load(f).get(args.numeric_mode, {}).get("dram_bytes_per_launch")
+                    pj = json.load(f).get(args.numeric_mode, {})
+                traffic = pj.get("dram_bytes_per_launch")
+                inst_per_step = pj.get("warp_inst_per_warp_step")
             except Exception:
                 traffic = None
         fp32_peak_tflops = 148 * 128 * 2 * (peak_json.get("sm_max_mhz", 1965.0) * 1e6) / 1e12
@@ -321,6 +324,15 @@ def run_ours(args):
                               "frac": flops / (kernel_ms * 1e-3) / 1e12 / fp32_peak_tflops, "flops_per_ray_step": 400,
                               "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz (non-tensor FP32, BASELINE.md §2)"},
         }
+        if inst_per_step:
+            # the binding limit: warp-instruction issue (1 per SMSP per clock).  Instructions per warp-ray-step come from the
+            # committed ncu capture of this kernel (profiles/trace_kernel_dram.json); time and clock are measured live.
+            sm_clock_hz = (clocks or {}).get("sm_mhz") or peak_json.get("sm_max_mhz", 1965.0)
+            issue_peak = 148 * 4 * sm_clock_hz * 1e6
+            issued = inst_per_step * (local["ray_steps"] / 32.0) / (kernel_ms * 1e-3)
+            line["roofline_issue"] = {"bound": "warp-instruction issue", "achieved": issued / 1e9, "peak": issue_peak / 1e9,
+                                      "unit": "G warp-inst/s", "frac": issued / issue_peak, "warp_inst_per_warp_ray_step": inst_per_step,
+                                      "peak_source": "148 SM x 4 schedulers x SM clock sampled during the run"}
         # CPU baseline beside it (N=1 only): bounded sample of the same workload
         if world == 1 and not args.no_cpu_baseline:
             try:
