@@ -68,6 +68,11 @@ SYMBOLS = {
     "bh_sky_pipeline_pass": (C.c_int, [_VP, _VP]),
     "bh_sky_pipeline_output": (_VP, [_VP]),
     "bh_sky_pipeline_read": (C.c_int, [_VP, _VP]),
+    "bh_post_pass_create": (C.c_int, [_VP, C.c_int, _U32, _U32, _VP, _U32, _U32, _VP, C.POINTER(_VP)]),
+    "bh_post_pass_destroy": (None, [_VP]),
+    "bh_post_pass_run": (C.c_int, [_VP, _VP, _VP]),
+    "bh_post_pass_output": (_VP, [_VP]),
+    "bh_post_pass_read": (C.c_int, [_VP, _VP]),
     "bh_model_load_obj": (C.c_int, [C.c_char_p, _VP, C.POINTER(ModelInfo)]),
     "bh_model_from_arrays": (C.c_int, [_VP, _I32, _VP, _I32, _VP, _I32, C.POINTER(C.c_float), _I32, _VP, C.POINTER(ModelInfo)]),
     "bh_model_build_bvh": (C.c_int, [_VP, _I32, C.POINTER(ModelInfo)]),

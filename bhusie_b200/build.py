@@ -17,7 +17,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libbhray.so")
 SOURCES = ["bh_abi.cu", "ray_kernels.cu", "model_host.cpp"]
-HEADERS = ["bh_device.h", "detmath.cuh", "ray_impl.cuh", os.path.join("..", "..", "include", "bh_abi.h")]
+HEADERS = ["bh_device.h", "detmath.cuh", "ray_impl.cuh", "post_impl.cuh", os.path.join("..", "..", "include", "bh_abi.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -568,6 +568,83 @@ int bh_sky_pipeline_read(bh_sky_pipeline *s, void *host_rgba)
     return BH_OK;
 }
 
+// ------------------------------------------------------------------------------------------ post chain
+struct bh_post_pass {
+    bh_ctx *ctx = nullptr;
+    int kind = 0;
+    uint32_t w = 0, h = 0, in_w = 0, in_h = 0;
+    const void *in1 = nullptr, *in2 = nullptr;
+    void *out = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool ran = false;
+    size_t out_bytes() const { return (size_t)w * h * (kind == BH_POST_FXAA ? 4 : 8); }
+};
+
+int bh_post_pass_create(bh_ctx *ctx, bh_post_kind kind, uint32_t out_w, uint32_t out_h, const void *in1_device, uint32_t in1_w,
+                        uint32_t in1_h, const void *in2_device, bh_post_pass **out)
+{
+    if (!out) { set_error("bh_post_pass_create: out is NULL"); return BH_ERR_INVALID; }
+    *out = nullptr;
+    if (!ctx || (int)kind < 0 || (int)kind > BH_POST_FXAA || !in1_device || out_w == 0 || out_h == 0 || in1_w == 0 || in1_h == 0 ||
+        out_w > 65535 || out_h > 65535 || ((uintptr_t)in1_device & 7u) || ((uintptr_t)in2_device & 7u)) {
+        set_error("bh_post_pass_create: bad argument");
+        return BH_ERR_INVALID;
+    }
+    if (kind == BH_POST_MIX && !in2_device) { set_error("bh_post_pass_create: MIX needs two inputs"); return BH_ERR_INVALID; }
+    if (kind >= BH_POST_MIX && (in1_w != out_w || in1_h != out_h)) { set_error("bh_post_pass_create: mix/hdr/fxaa run at their input's resolution"); return BH_ERR_INVALID; }
+    BH_CUDA(cudaSetDevice(ctx->device));
+    bh_post_pass *p = new (std::nothrow) bh_post_pass();
+    if (!p) { set_error("bh_post_pass_create: out of host memory"); return BH_ERR_NOMEM; }
+    p->ctx = ctx; p->kind = (int)kind; p->w = out_w; p->h = out_h; p->in_w = in1_w; p->in_h = in1_h; p->in1 = in1_device; p->in2 = in2_device;
+    cudaError_t e = cudaMalloc(&p->out, p->out_bytes());
+    if (e != cudaSuccess) { delete p; return cuda_fail(e, "bh_post_pass_create: cudaMalloc"); }
+    *out = p;
+    return BH_OK;
+}
+
+void bh_post_pass_destroy(bh_post_pass *p)
+{
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    if (p->ran) cudaStreamSynchronize(p->last_stream);
+    if (p->out) cudaFree(p->out);
+    delete p;
+}
+
+int bh_post_pass_run(bh_post_pass *p, const void *details, void *cuda_stream)
+{
+    if (!p) { set_error("bh_post_pass_run: NULL pass"); return BH_ERR_INVALID; }
+    if ((p->kind == BH_POST_MIX || p->kind == BH_POST_FXAA) && !details) { set_error("bh_post_pass_run: this pass needs its details uniform"); return BH_ERR_INVALID; }
+    BH_CUDA(cudaSetDevice(p->ctx->device));
+    PostParams P;
+    memset(&P, 0, sizeof P);
+    P.in1 = HalfImage{ static_cast<const uint2 *>(p->in1), (int)p->in_w, (int)p->in_h };
+    P.in2 = HalfImage{ static_cast<const uint2 *>(p->in2), (int)p->in_w, (int)p->in_h };
+    P.out = p->out; P.w = (int)p->w; P.h = (int)p->h;
+    if (p->kind == BH_POST_MIX) P.mix_ratio = static_cast<const bh_mix_details *>(details)->mix_ratio;
+    if (p->kind == BH_POST_FXAA) {
+        const bh_fxaa_details *d = static_cast<const bh_fxaa_details *>(details);
+        P.edge_min = d->edge_threshold_min; P.edge_max = d->edge_threshold_max; P.iterations = d->iterations; P.subpix = d->subpixel_quality;
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    LaunchConfig cfg{ p->ctx->sm_count, p->ctx->numeric_mode };
+    p->last_stream = stream; p->ran = true;
+    BH_CUDA(launch_post_pass(p->kind, P, cfg, stream));
+    return BH_OK;
+}
+
+const void *bh_post_pass_output(const bh_post_pass *p) { return p ? p->out : nullptr; }
+
+int bh_post_pass_read(bh_post_pass *p, void *host)
+{
+    if (!p || !host) { set_error("bh_post_pass_read: NULL argument"); return BH_ERR_INVALID; }
+    if (!p->ran) { set_error("bh_post_pass_read: the pass has not run"); return BH_ERR_STATE; }
+    BH_CUDA(cudaSetDevice(p->ctx->device));
+    BH_CUDA(cudaStreamSynchronize(p->last_stream));
+    BH_CUDA(cudaMemcpy(host, p->out, p->out_bytes(), cudaMemcpyDeviceToHost));
+    return BH_OK;
+}
+
 // ------------------------------------------------------------------------------------------ math probe
 int bh_ctx_math_probe(bh_ctx *ctx, int fn, const float *host_a, const float *host_b, float *host_out, size_t n)
 {

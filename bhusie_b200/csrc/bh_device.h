@@ -63,6 +63,18 @@ struct SkyParams {
     unsigned long long *stats;
 };
 
+// ---- post chain
+struct HalfImage { const uint2 *px; int w, h; };     // RGBA16F, 8 B per texel
+
+struct PostParams {
+    HalfImage in1, in2;
+    void *out;                       // RGBA16F (uint2 per pixel); FXAA: RGBA8 sRGB (uint per pixel)
+    int w, h;
+    float mix_ratio;                 // MixDetails (mix_pipeline.rs:5-7)
+    float edge_min, edge_max, subpix;    // FXAADetailsUniform (fxaa_pipline.rs:74-80)
+    int iterations;
+};
+
 struct LaunchConfig {
     int sm_count;
     int numeric_mode;                // bh_numeric_mode
@@ -73,6 +85,7 @@ cudaError_t launch_ray_pass(const PassParams &p, const LaunchConfig &cfg, cudaSt
 // base level only: trace the tile range [p.item_begin, p.n_items) without resetting the pass statistics
 cudaError_t launch_trace_range(const PassParams &p, const LaunchConfig &cfg, bool reset_stats, cudaStream_t stream);
 cudaError_t launch_sky_pass(const SkyParams &p, const LaunchConfig &cfg, cudaStream_t stream);
+cudaError_t launch_post_pass(int kind, const PostParams &p, const LaunchConfig &cfg, cudaStream_t stream);
 cudaError_t launch_math_probe(int fn, const float *a, const float *b, float *out, size_t n, cudaStream_t stream);
 
 }  // namespace bh

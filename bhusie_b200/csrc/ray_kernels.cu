@@ -61,11 +61,13 @@ constexpr int kTopBytes = kTopHeaderBytes + kTopNodes * 32;
 #define BH_NUM_NS lit
 #define BH_FUSED 0
 #include "ray_impl.cuh"
+#include "post_impl.cuh"
 #undef BH_NUM_NS
 #undef BH_FUSED
 #define BH_NUM_NS fus
 #define BH_FUSED 1
 #include "ray_impl.cuh"
+#include "post_impl.cuh"
 #undef BH_NUM_NS
 #undef BH_FUSED
 
@@ -160,6 +162,21 @@ cudaError_t launch_sky_pass(const SkyParams &s, const LaunchConfig &cfg, cudaStr
     if (grid == 0) grid = 1;
     if (cfg.numeric_mode == BH_NUMERIC_LITERAL) lit::sky_kernel<<<grid, 256, 0, stream>>>(s);
     else fus::sky_kernel<<<grid, 256, 0, stream>>>(s);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_post_pass(int kind, const PostParams &p, const LaunchConfig &cfg, cudaStream_t stream)
+{
+    const dim3 grid((unsigned)((p.w + 31) / 32), (unsigned)((p.h + 7) / 8));
+    const bool lit_mode = cfg.numeric_mode == BH_NUMERIC_LITERAL;
+    switch (kind) {
+    case BH_POST_BLOOM_DOWN: if (lit_mode) lit::bloom_down_kernel<<<grid, 256, 0, stream>>>(p); else fus::bloom_down_kernel<<<grid, 256, 0, stream>>>(p); break;
+    case BH_POST_BLOOM_UP:   if (lit_mode) lit::bloom_up_kernel<<<grid, 256, 0, stream>>>(p);   else fus::bloom_up_kernel<<<grid, 256, 0, stream>>>(p); break;
+    case BH_POST_MIX:        if (lit_mode) lit::mix_kernel<<<grid, 256, 0, stream>>>(p);        else fus::mix_kernel<<<grid, 256, 0, stream>>>(p); break;
+    case BH_POST_HDR:        if (lit_mode) lit::hdr_kernel<<<grid, 256, 0, stream>>>(p);        else fus::hdr_kernel<<<grid, 256, 0, stream>>>(p); break;
+    case BH_POST_FXAA:       if (lit_mode) lit::fxaa_kernel<<<grid, 256, 0, stream>>>(p);       else fus::fxaa_kernel<<<grid, 256, 0, stream>>>(p); break;
+    default: return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
 

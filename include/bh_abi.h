@@ -202,6 +202,27 @@ int  bh_sky_pipeline_pass(bh_sky_pipeline *p, void *cuda_stream);
 const void *bh_sky_pipeline_output(const bh_sky_pipeline *p);
 int  bh_sky_pipeline_read(bh_sky_pipeline *p, void *host_rgba);   /* local_rows*width*(8|16) B */
 
+/* ---- post chain: the passes that consume the sky pass's output.  One object per pass, the same
+ *      new / pass / output_view triple as the reference's BloomPipeline (bloom_pipline.rs:20,156,160; shaders
+ *      bloom_down.wgsl / bloom_up.wgsl), MixPipeline (mix_pipeline.rs:24; mix.wgsl), HDRPipeline (hdr_pipeline.rs;
+ *      hdr.wgsl ACES) and FXAAPipeline (fxaa_pipline.rs; fxaa.wgsl).  Inputs and outputs are device images:
+ *      RGBA16F (8 B/pixel) everywhere, RGBA8 with sRGB-encoded rgb (4 B/pixel) out of FXAA (fxaa_pipline.rs:120). ---- */
+typedef enum bh_post_kind {
+    BH_POST_BLOOM_DOWN = 0, BH_POST_BLOOM_UP = 1, BH_POST_MIX = 2, BH_POST_HDR = 3, BH_POST_FXAA = 4
+} bh_post_kind;
+typedef struct bh_mix_details  { float mix_ratio; } bh_mix_details;                       /* mix_pipeline.rs:5-7  */
+typedef struct bh_fxaa_details { float edge_threshold_min, edge_threshold_max; int32_t iterations; float subpixel_quality; } bh_fxaa_details; /* fxaa_pipline.rs:74-80 */
+typedef struct bh_post_pass bh_post_pass;
+/* in1: the pass's input image (MIX: texture_view_1, the sky output); in2: MIX only (texture_view_2, the bloom output),
+ * same size as in1 and as the output.  The pass allocates its own out_w x out_h output. */
+int  bh_post_pass_create(bh_ctx *ctx, bh_post_kind kind, uint32_t out_w, uint32_t out_h,
+                         const void *in1_device, uint32_t in1_w, uint32_t in1_h, const void *in2_device, bh_post_pass **out);
+void bh_post_pass_destroy(bh_post_pass *p);
+/* details: bh_mix_details for MIX, bh_fxaa_details for FXAA (host bytes, read before return), NULL otherwise */
+int  bh_post_pass_run(bh_post_pass *p, const void *details, void *cuda_stream);
+const void *bh_post_pass_output(const bh_post_pass *p);
+int  bh_post_pass_read(bh_post_pass *p, void *host);
+
 /* ---- host-side scene preparation: replaces load_model + Model::build_bvh ---------------------
  * (src/renderer/model.rs:7-87, src/renderer/triangle.rs:143-259).  Pure host code; `model_uniform`
  * is a caller-owned BH_MODEL_UNIFORM_SIZE-byte buffer that receives the verbatim ModelUniform. */

@@ -1132,6 +1132,8 @@ int64_t bho_load_obj(const char *path, uint8_t *model_uniform, int32_t *point_co
     return triangle_count;
 }
 
+#include "bh_oracle_post.inc"   /* post chain: bloom, mix, ACES, FXAA */
+
 /* ------------------------------------------------------------------ leaf-function entry points for KATs */
 void bho_kat_euler(const uint8_t *black_hole132, const float *pos_dir6, float step, float *out6)
 {

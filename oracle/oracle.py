@@ -45,7 +45,7 @@ FLAVOURS = ("strict", "contract", "fused")
 def build(force: bool = False) -> None:
     """Compile both flavours with oracle/Makefile (gcc, -ffp-contract=off, OpenMP)."""
     libs = [os.path.join(_HERE, "lib", f"libbh_oracle_{f}.so") for f in FLAVOURS]
-    srcs = [os.path.join(_HERE, n) for n in ("bh_oracle.c", "bho_math.h", "Makefile")]
+    srcs = [os.path.join(_HERE, n) for n in ("bh_oracle.c", "bho_math.h", "bh_oracle_post.inc", "Makefile")]
     stale = force or any(not os.path.exists(l) for l in libs) or \
         max(os.path.getmtime(s) for s in srcs) > min(os.path.getmtime(l) for l in libs)
     if stale:
@@ -65,6 +65,8 @@ def _lib(flavour: str) -> C.CDLL:
         lib = C.CDLL(path)
         lib.bho_ray_pass.restype = C.c_int
         lib.bho_sky_pass.restype = C.c_int
+        for n in ("bho_bloom_down", "bho_bloom_up", "bho_mix", "bho_hdr", "bho_fxaa"):
+            getattr(lib, n).restype = C.c_int
         lib.bho_build_bvh.restype = C.c_int64
         lib.bho_load_obj.restype = C.c_int64
         for n in ("pow",):
@@ -167,6 +169,71 @@ def sky_pass(scene: OracleScene, prev: np.ndarray, flavour: str = "strict", nthr
     if rc != 0:
         raise RuntimeError(f"bho_sky_pass failed: {rc}")
     return o32, o16, {n: int(getattr(cnt, n)) for n in COUNTER_FIELDS}
+
+
+# ---------------------------------------------------------------- post chain
+def _h16(a) -> np.ndarray:
+    a = np.asarray(a)
+    if a.dtype == np.float16:
+        a = a.view(np.uint16)
+    assert a.dtype == np.uint16 and a.ndim == 3 and a.shape[2] == 4
+    return np.ascontiguousarray(a)
+
+
+def bloom(src, out_w: int, out_h: int, direction: str, flavour: str = "strict") -> np.ndarray:
+    """bloom_down.wgsl / bloom_up.wgsl on an RGBA16F image (uint16 bits or float16); returns uint16 bits (h, w, 4)."""
+    s = _h16(src)
+    dst = np.zeros((out_h, out_w, 4), np.uint16)
+    fn = getattr(_lib(flavour), "bho_bloom_down" if direction == "down" else "bho_bloom_up")
+    rc = fn(_p(s), C.c_int32(s.shape[1]), C.c_int32(s.shape[0]), _p(dst), C.c_int32(out_w), C.c_int32(out_h))
+    if rc != 0:
+        raise RuntimeError(f"bho_bloom_{direction} failed: {rc}")
+    return dst
+
+
+def mix(in1, in2, mix_ratio: float = 0.7, flavour: str = "strict") -> np.ndarray:
+    a, b = _h16(in1), _h16(in2)
+    assert a.shape == b.shape
+    dst = np.zeros_like(a)
+    rc = _lib(flavour).bho_mix(_p(a), _p(b), C.c_int32(a.shape[1]), C.c_int32(a.shape[0]), C.c_float(mix_ratio), _p(dst))
+    if rc != 0:
+        raise RuntimeError(f"bho_mix failed: {rc}")
+    return dst
+
+
+def hdr(src, flavour: str = "strict") -> np.ndarray:
+    s = _h16(src)
+    dst = np.zeros_like(s)
+    rc = _lib(flavour).bho_hdr(_p(s), C.c_int32(s.shape[1]), C.c_int32(s.shape[0]), _p(dst))
+    if rc != 0:
+        raise RuntimeError(f"bho_hdr failed: {rc}")
+    return dst
+
+
+def fxaa(src, details: bytes, flavour: str = "strict") -> np.ndarray:
+    """fxaa.wgsl -> RGBA8 (sRGB-encoded rgb, linear alpha), uint8 (h, w, 4)."""
+    s = _h16(src)
+    assert len(details) == 16
+    dst = np.zeros(s.shape, np.uint8)
+    rc = _lib(flavour).bho_fxaa(_p(s), C.c_int32(s.shape[1]), C.c_int32(s.shape[0]), C.c_char_p(bytes(details)), _p(dst))
+    if rc != 0:
+        raise RuntimeError(f"bho_fxaa failed: {rc}")
+    return dst
+
+
+def post_chain(sky16, sizes, mix_ratio: float, fxaa_details: bytes, flavour: str = "strict") -> dict:
+    """The whole chain of mod.rs:219-312 / 425-431: bloom down xN, up xN, mix, ACES, FXAA.  `sizes` = the 2N bloom
+    resolutions [(w,h), ...].  Returns every stage's output."""
+    out = {"bloom": []}
+    cur = _h16(sky16)
+    n = len(sizes) // 2
+    for i, (w, h) in enumerate(sizes):
+        cur = bloom(cur, w, h, "down" if i < n else "up", flavour)
+        out["bloom"].append(cur)
+    out["mix"] = mix(sky16, cur, mix_ratio, flavour)
+    out["hdr"] = hdr(out["mix"], flavour)
+    out["fxaa"] = fxaa(out["hdr"], fxaa_details, flavour)
+    return out
 
 
 def new_model_blob() -> np.ndarray:
