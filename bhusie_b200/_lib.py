@@ -41,6 +41,7 @@ SYMBOLS = {
     "bh_ctx_set_numeric_mode": (C.c_int, [_VP, C.c_int]),
     "bh_ctx_get_numeric_mode": (C.c_int, [_VP]),
     "bh_ctx_set_texture": (C.c_int, [_VP, C.c_int, _VP, _U32, _U32]),
+    "bh_ctx_generate_disk_texture": (C.c_int, [_VP, _U32, _U32, _VP, C.c_int]),
     "bh_ctx_upload_models": (C.c_int, [_VP, _VP, C.c_size_t]),
     "bh_ctx_upload_models_async": (C.c_int, [_VP, _VP, C.c_size_t, _VP]),
     "bh_ctx_set_model_header": (C.c_int, [_VP, _U32, C.POINTER(C.c_float), _I32]),
@@ -76,6 +77,7 @@ SYMBOLS = {
     "bh_model_load_obj": (C.c_int, [C.c_char_p, _VP, C.POINTER(ModelInfo)]),
     "bh_model_from_arrays": (C.c_int, [_VP, _I32, _VP, _I32, _VP, _I32, C.POINTER(C.c_float), _I32, _VP, C.POINTER(ModelInfo)]),
     "bh_model_build_bvh": (C.c_int, [_VP, _I32, C.POINTER(ModelInfo)]),
+    "bh_save_png": (C.c_int, [C.c_char_p, _VP, _U32, _U32, C.c_int]),
     "bh_ctx_math_probe": (C.c_int, [_VP, C.c_int, _VP, _VP, _VP, C.c_size_t]),
 }
 

@@ -24,7 +24,7 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",
     "--fmad=false", "-prec-div=true", "-prec-sqrt=true",
     "-Xcompiler", "-fPIC,-O2,-fno-fast-math,-ffp-contract=off",
-    "-shared", "-cudart", "static",
+    "-shared", "-cudart", "static", "-lz",
 ]
 
 

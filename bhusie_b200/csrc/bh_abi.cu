@@ -192,6 +192,25 @@ int bh_ctx_set_texture(bh_ctx *ctx, bh_texture_slot slot, const uint8_t *rgba8, 
     return BH_OK;
 }
 
+int bh_ctx_generate_disk_texture(bh_ctx *ctx, uint32_t w, uint32_t h, uint8_t *host_rgba8, int install)
+{
+    if (!ctx || w == 0 || h == 0 || w > 32768 || h > 32768) { set_error("bh_ctx_generate_disk_texture: bad argument"); return BH_ERR_INVALID; }
+    BH_CUDA(cudaSetDevice(ctx->device));
+    uchar4 *dev = nullptr;
+    BH_CUDA(cudaMalloc(&dev, (size_t)w * h * 4));
+    cudaError_t e = launch_disk_texture((int)w, (int)h, dev, nullptr);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
+    if (e == cudaSuccess && host_rgba8) e = cudaMemcpy(host_rgba8, dev, (size_t)w * h * 4, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { cudaFree(dev); return cuda_fail(e, "bh_ctx_generate_disk_texture"); }
+    if (install) {
+        if (ctx->tex[BH_TEX_DISK]) cudaFree(ctx->tex[BH_TEX_DISK]);
+        ctx->tex[BH_TEX_DISK] = dev; ctx->tex_w[BH_TEX_DISK] = (int)w; ctx->tex_h[BH_TEX_DISK] = (int)h;
+    } else {
+        cudaFree(dev);
+    }
+    return BH_OK;
+}
+
 static int upload_models(bh_ctx *ctx, const void *bytes, size_t nbytes, bool async, cudaStream_t stream)
 {
     if (!ctx || (!bytes && nbytes) || nbytes % BH_MODEL_UNIFORM_SIZE != 0 || nbytes / BH_MODEL_UNIFORM_SIZE > BH_MAX_MODELS) {

@@ -86,6 +86,7 @@ cudaError_t launch_ray_pass(const PassParams &p, const LaunchConfig &cfg, cudaSt
 cudaError_t launch_trace_range(const PassParams &p, const LaunchConfig &cfg, bool reset_stats, cudaStream_t stream);
 cudaError_t launch_sky_pass(const SkyParams &p, const LaunchConfig &cfg, cudaStream_t stream);
 cudaError_t launch_post_pass(int kind, const PostParams &p, const LaunchConfig &cfg, cudaStream_t stream);
+cudaError_t launch_disk_texture(int w, int h, uchar4 *out, cudaStream_t stream);
 cudaError_t launch_math_probe(int fn, const float *a, const float *b, float *out, size_t n, cudaStream_t stream);
 
 }  // namespace bh

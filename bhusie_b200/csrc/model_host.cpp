@@ -22,6 +22,8 @@
 #include <unordered_map>
 #include <vector>
 
+#include <zlib.h>
+
 #include "../../include/bh_abi.h"
 
 namespace bh {
@@ -328,4 +330,52 @@ extern "C" int bh_model_load_obj(const char *path, void *model_uniform, bh_model
     const int rc = build_bvh(model_uniform, triangle_count, info);
     if (rc == BH_OK && info) { info->point_count = point_count; info->normal_count = normal_count; }
     return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Frame dump: the "Save Image" path of Renderer::render (src/renderer/mod.rs:460-486) — the post-FXAA
+// RGBA8 frame written as an 8-bit RGBA PNG with alpha forced to 255 (mod.rs:479).  The reference's 256-byte row-pitch
+// staging buffer (mod.rs:491-526) is a wgpu copy constraint and has no counterpart here.  zlib is the only dependency.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+void png_chunk(FILE *f, const char type[4], const unsigned char *data, size_t n)
+{
+    unsigned char len[4] = { (unsigned char)(n >> 24), (unsigned char)(n >> 16), (unsigned char)(n >> 8), (unsigned char)n };
+    std::fwrite(len, 1, 4, f);
+    std::fwrite(type, 1, 4, f);
+    if (n) std::fwrite(data, 1, n, f);
+    uLong crc = crc32(0L, reinterpret_cast<const Bytef *>(type), 4);
+    if (n) crc = crc32(crc, data, static_cast<uInt>(n));
+    unsigned char c[4] = { (unsigned char)(crc >> 24), (unsigned char)(crc >> 16), (unsigned char)(crc >> 8), (unsigned char)crc };
+    std::fwrite(c, 1, 4, f);
+}
+}  // namespace
+
+extern "C" int bh_save_png(const char *path, const uint8_t *rgba8, uint32_t w, uint32_t h, int force_opaque)
+{
+    if (!path || !rgba8 || w == 0 || h == 0 || w > 65535 || h > 65535) { bh::set_error("bh_save_png: bad argument"); return BH_ERR_INVALID; }
+    std::vector<unsigned char> raw((size_t)h * ((size_t)w * 4 + 1));
+    for (uint32_t y = 0; y < h; ++y) {
+        unsigned char *row = raw.data() + (size_t)y * ((size_t)w * 4 + 1);
+        row[0] = 0;                                               // filter type None
+        std::memcpy(row + 1, rgba8 + (size_t)y * w * 4, (size_t)w * 4);
+        if (force_opaque) for (uint32_t x = 0; x < w; ++x) row[1 + 4 * (size_t)x + 3] = 255;
+    }
+    uLongf zn = compressBound(static_cast<uLong>(raw.size()));
+    std::vector<unsigned char> z(zn);
+    if (compress2(z.data(), &zn, raw.data(), static_cast<uLong>(raw.size()), 6) != Z_OK) { bh::set_error("bh_save_png: zlib failed"); return BH_ERR_NOMEM; }
+    FILE *f = std::fopen(path, "wb");
+    if (!f) { bh::set_error("bh_save_png: cannot open %s for writing", path); return BH_ERR_NOENT; }
+    static const unsigned char sig[8] = { 0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a };
+    std::fwrite(sig, 1, 8, f);
+    unsigned char ihdr[13] = { (unsigned char)(w >> 24), (unsigned char)(w >> 16), (unsigned char)(w >> 8), (unsigned char)w,
+                               (unsigned char)(h >> 24), (unsigned char)(h >> 16), (unsigned char)(h >> 8), (unsigned char)h,
+                               8, 6, 0, 0, 0 };                  // 8-bit, colour type 6 (RGBA)
+    png_chunk(f, "IHDR", ihdr, 13);
+    png_chunk(f, "IDAT", z.data(), zn);
+    png_chunk(f, "IEND", nullptr, 0);
+    const bool ok = std::ferror(f) == 0;
+    std::fclose(f);
+    if (!ok) { bh::set_error("bh_save_png: write error on %s", path); return BH_ERR_CUDA; }
+    return BH_OK;
 }

@@ -72,6 +72,70 @@ constexpr int kTopBytes = kTopHeaderBytes + kTopNodes * 32;
 #undef BH_FUSED
 
 namespace {
+// ------------------------------------------------------------------------------------------------
+// disk texture generator: perlin/src/main.rs:6-148, the offline tool behind disk.png.
+// Rust never contracts f32 arithmetic, so this kernel is numeric-mode independent: plain IEEE ops (the TU is
+// compiled with --fmad=false) and det-math transcendentals.  One thread per texel: the spiral map is the same for
+// all four octaves, so the multi-pass generate -> spiral -> merge of the tool collapses into one gather-free pass.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned rotl32(unsigned v, unsigned s) { return (v << s) | (v >> (32u - s)); }
+__device__ __forceinline__ unsigned sat_u8(float v) { return !(v == v) ? 0u : (v <= 0.0f ? 0u : (v >= 255.0f ? 255u : (unsigned)v)); }
+__device__ __forceinline__ unsigned sat_u32(float v) { return !(v == v) ? 0u : (v <= 0.0f ? 0u : (v >= 4294967296.0f ? 4294967295u : (unsigned)v)); }
+
+__device__ __forceinline__ float dot_grid_gradient(unsigned ix, unsigned iy, float x, float y)      // main.rs:6-32
+{
+    unsigned a = ix, b = iy;
+    a *= 3284157443u;
+    b ^= rotl32(a, 16);
+    b *= 1911520717u;
+    a ^= rotl32(b, 16);
+    a *= 2048419325u;
+    const float random = (float)a * (3.14159265358979323846f / (float)0xffffffffu);
+    float gx, gy;
+    detmath::sincos_f(random, gy, gx);
+    const float dx = x - (float)ix, dy = y - (float)iy;
+    return dx * gx + dy * gy;
+}
+__device__ __forceinline__ float perlin_interp(float a0, float a1, float w)                          // main.rs:34-37
+{
+    return (a1 - a0) * ((w * (w * 6.0f - 15.0f) + 10.0f) * w * w * w) + a0;
+}
+__device__ float perlin2(float x, float y)                                                            // main.rs:39-57
+{
+    const unsigned x0 = sat_u32(floorf(x)), x1 = x0 + 1u, y0 = sat_u32(floorf(y)), y1 = y0 + 1u;
+    const float sx = x - (float)x0, sy = y - (float)y0;
+    float n0 = dot_grid_gradient(x0, y0, x, y), n1 = dot_grid_gradient(x1, y0, x, y);
+    const float ix0 = perlin_interp(n0, n1, sx);
+    n0 = dot_grid_gradient(x0, y1, x, y); n1 = dot_grid_gradient(x1, y1, x, y);
+    const float ix1 = perlin_interp(n0, n1, sx);
+    return perlin_interp(ix0, ix1, sy) * 0.5f + 0.5f;
+}
+
+__global__ void __launch_bounds__(256) disk_texture_kernel(int w, int h, uchar4 *out)
+{
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= w || y >= h) return;
+    const float PI32 = 3.14159265358979323846f;
+    // spiral(amount 2, power 0.5), main.rs:79-110
+    const float rx = ((float)x / (float)w) * 2.0f - 1.0f, ry = ((float)y / (float)h) * 2.0f - 1.0f;
+    const float r = sqrtf(rx * rx + ry * ry);
+    float theta = detmath::atan2_f(ry, rx);
+    theta = fmodf(theta + PI32 + detmath::pow_f(r, 0.5f) * PI32 * 2.0f, 2.0f * PI32) - PI32;
+    float sn, cs;
+    detmath::sincos_f(theta, sn, cs);
+    const unsigned nx = sat_u32((r * cs * 0.5f + 0.5f) * (float)w) % (unsigned)w;
+    const unsigned ny = sat_u32((r * sn * 0.5f + 0.5f) * (float)h) % (unsigned)h;
+    // generate() at the warped texel for the four densities (main.rs:60-77,134-141), merged finest-first (143-145)
+    const float dens[4] = { 4.0f / (float)w, 20.0f / (float)w, 50.0f / (float)w, 100.0f / (float)w };
+    unsigned v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = sat_u8(perlin2((float)nx * dens[k], (float)ny * dens[k]) * 256.0f);
+    unsigned m = sat_u8((float)v[3] * 0.5f + (float)v[2] * (1.0f - 0.5f));
+    m = sat_u8((float)m * 0.5f + (float)v[1] * (1.0f - 0.5f));
+    m = sat_u8((float)m * 0.5f + (float)v[0] * (1.0f - 0.5f));
+    out[(size_t)y * (size_t)w + (size_t)x] = make_uchar4((unsigned char)m, (unsigned char)m, (unsigned char)m, (unsigned char)m);
+}
+
 __global__ void math_probe_kernel(int fn, const float *a, const float *b, float *out, size_t n)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -177,6 +241,13 @@ cudaError_t launch_post_pass(int kind, const PostParams &p, const LaunchConfig &
     case BH_POST_FXAA:       if (lit_mode) lit::fxaa_kernel<<<grid, 256, 0, stream>>>(p);       else fus::fxaa_kernel<<<grid, 256, 0, stream>>>(p); break;
     default: return cudaErrorInvalidValue;
     }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_disk_texture(int w, int h, uchar4 *out, cudaStream_t stream)
+{
+    const dim3 grid((unsigned)((w + 31) / 32), (unsigned)((h + 7) / 8));
+    disk_texture_kernel<<<grid, 256, 0, stream>>>(w, h, out);
     return cudaGetLastError();
 }
 

@@ -86,6 +86,12 @@ class Context:
         self.set_texture(TEX_DISK, tex["disk"])
         self.set_texture(TEX_SKY, tex["sky"])
 
+    def generate_disk_texture(self, w: int = 1000, h: int = 1000, install: bool = True) -> np.ndarray:
+        """perlin/src/main.rs on the GPU: returns the (h, w, 4) RGBA8 texels and (install) binds them as the disk texture."""
+        out = np.empty((h, w, 4), np.uint8)
+        _lib.check(self._lib.bh_ctx_generate_disk_texture(self._h, w, h, out.ctypes.data_as(C.c_void_p), 1 if install else 0))
+        return out
+
     def upload_models(self, blob: np.ndarray | None):
         if blob is None:
             self.model_count = 0

@@ -55,6 +55,14 @@ def bloom_sizes(resolution=(1918, 1081), count: int = 5, multiplier: float = 2.0
     return out
 
 
+def save_png(path: str, rgba8: np.ndarray, force_opaque: bool = True):
+    """Renderer's "Save Image" (mod.rs:460-486): RGBA8 frame -> PNG through the library's host code."""
+    a = np.ascontiguousarray(rgba8, dtype=np.uint8)
+    if a.ndim != 3 or a.shape[2] != 4:
+        raise ValueError("frame must be (h, w, 4) uint8")
+    _lib.check(_lib.load().bh_save_png(path.encode(), a.ctypes.data_as(C.c_void_p), a.shape[1], a.shape[0], 1 if force_opaque else 0))
+
+
 class _PostPass:
     def __init__(self, ctx, kind: int, resolution, view1, view2=None):
         self._lib = ctx._lib

@@ -107,6 +107,12 @@ int  bh_ctx_get_numeric_mode(const bh_ctx *ctx);
  * (no sRGB), bilinear, clamp-to-edge, one mip.  Copies rgba8 (w*h*4 bytes) to the device. */
 int  bh_ctx_set_texture(bh_ctx *ctx, bh_texture_slot slot, const uint8_t *rgba8, uint32_t w, uint32_t h);
 
+/* SURVEY §8 f4 — the reference's offline generator of disk.png (perlin/src/main.rs:6-148: 4 octaves of hash-gradient
+ * Perlin noise, spiral-warped, merged) run on the GPU: w x h RGBA8 with r=g=b=a (the tool uses 1000 x 1000).
+ * host_rgba8 (nullable) receives the texels; install != 0 also makes it the context's BH_TEX_DISK, so a scene needs
+ * no binary disk asset. */
+int  bh_ctx_generate_disk_texture(bh_ctx *ctx, uint32_t w, uint32_t h, uint8_t *host_rgba8, int install);
+
 /* ModelArrayBuffer::update_buffer (src/renderer/array_buffer.rs:71-79): `bytes` is
  * ModelUniform[count] verbatim, nbytes == count*BH_MODEL_UNIFORM_SIZE, count <= BH_MAX_MODELS.
  * Synchronous (returns after the copy).  bh_ctx_upload_models_async enqueues the same copy on
@@ -236,6 +242,10 @@ int  bh_model_from_arrays(const float *points, int32_t n_points, const float *no
                           const int32_t *tris, int32_t n_tris, const float position[3], int32_t visible,
                           void *model_uniform, bh_model_info *info);
 int  bh_model_build_bvh(void *model_uniform, int32_t triangle_count, bh_model_info *info);
+
+/* ---- frame dump: the reference's "Save Image" (src/renderer/mod.rs:460-486): RGBA8 -> PNG, alpha
+ *      forced to 255 when force_opaque != 0 (mod.rs:479 writes 255).  Pure host code. ------------------------------ */
+int  bh_save_png(const char *path, const uint8_t *rgba8, uint32_t w, uint32_t h, int force_opaque);
 
 /* ---- device math probe (tests only): evaluates the kernel's det-math on the device so that
  *      tests can compare it bit-for-bit with the oracle's contract flavour.

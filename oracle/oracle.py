@@ -236,6 +236,17 @@ def post_chain(sky16, sizes, mix_ratio: float, fxaa_details: bytes, flavour: str
     return out
 
 
+def disk_texture(w: int = 1000, h: int = 1000, flavour: str = "strict") -> np.ndarray:
+    """perlin/src/main.rs: the generator of disk.png -> (h, w, 4) uint8 with r=g=b=a."""
+    out = np.zeros((h, w, 4), np.uint8)
+    lib = _lib(flavour)
+    lib.bho_disk_texture.restype = C.c_int
+    rc = lib.bho_disk_texture(C.c_int32(w), C.c_int32(h), _p(out))
+    if rc != 0:
+        raise RuntimeError(f"bho_disk_texture failed: {rc}")
+    return out
+
+
 def new_model_blob() -> np.ndarray:
     return np.zeros(MU_SIZE, np.uint8)
 
