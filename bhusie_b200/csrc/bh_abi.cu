@@ -419,6 +419,7 @@ int bh_ray_pipeline_pass_to_host(bh_ray_pipeline *p, const bh_camera_uniform *ca
     const int rc = build_pass_params(p, camera, black_hole, details, "bh_ray_pipeline_pass_to_host", P);
     if (rc != BH_OK) return rc;
     if (!pinned_host_rgba32f) { set_error("bh_ray_pipeline_pass_to_host: host buffer is NULL"); return BH_ERR_INVALID; }
+    if (p->bound_frame) { set_error("bh_ray_pipeline_pass_to_host: output is bound to an external frame (bh_ray_pipeline_bind_frame)"); return BH_ERR_STATE; }
     if (n_chunks == 0) n_chunks = 1;
     if (n_chunks > 16) n_chunks = 16;
     bh_ctx *c = p->ctx;

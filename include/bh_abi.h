@@ -91,7 +91,7 @@ const char *bh_last_error(void);            /* thread-local text of the last fai
 /* ---- context: replaces the wgpu Device/Queue pair + Renderer-owned scene buffers
  *      (src/renderer/mod.rs:63-89,113-114) ---------------------------------------------------- */
 int  bh_ctx_create(int cuda_device, bh_ctx **out);
-void bh_ctx_destroy(bh_ctx *ctx);
+void bh_ctx_destroy(bh_ctx *ctx);            /* destroy every pipeline / post pass of the context first */
 
 /* Numeric mode of every kernel launched through this context.  WGSL leaves contraction and the
  * rounding of `/` (2.5 ulp) to the shader compiler; the two modes are the two ends of that latitude:
