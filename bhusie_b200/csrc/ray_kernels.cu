@@ -168,10 +168,10 @@ static cudaError_t launch_trace(K kernel, bool queue, const PassParams &p, const
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     unsigned grid = (unsigned)(cfg.sm_count * per_sm);      // persistent: one wave of resident CTAs
-    if (!queue) {
-        const unsigned need = (p.n_items - p.item_begin + 3u) / 4u;
-        if (need < grid) grid = need ? need : 1u;
-    }
+    // never more CTAs than there can be work: tile mode knows the item count, queue mode its upper bound
+    const unsigned items = queue ? (unsigned)(((size_t)p.local_rows * (size_t)p.w + 31) / 32) : p.n_items - p.item_begin;
+    const unsigned need = (items + 3u) / 4u;
+    if (need < grid) grid = need ? need : 1u;
     kernel<<<grid, 128, 0, stream>>>(p);
     return cudaGetLastError();
 }
@@ -180,11 +180,19 @@ template <bool QUEUE>
 static cudaError_t launch_trace_mode(const PassParams &p, const LaunchConfig &cfg, cudaStream_t stream)
 {
     const bool euler = p.det.integration_method == 0;
-    if (cfg.numeric_mode == BH_NUMERIC_LITERAL)
-        return euler ? launch_trace(lit::trace_kernel<0, QUEUE>, QUEUE, p, cfg, stream)
-                     : launch_trace(lit::trace_kernel<1, QUEUE>, QUEUE, p, cfg, stream);
-    return euler ? launch_trace(fus::trace_kernel<0, QUEUE>, QUEUE, p, cfg, stream)
-                 : launch_trace(fus::trace_kernel<1, QUEUE>, QUEUE, p, cfg, stream);
+    // high-occupancy build only when every warp of it would still get several items (tile mode knows the count)
+    const unsigned warps_hi = (unsigned)cfg.sm_count * 4u * (euler ? 8u : 5u);
+    const bool hi = !QUEUE && (p.n_items - p.item_begin) >= 6u * warps_hi;
+    if (cfg.numeric_mode == BH_NUMERIC_LITERAL) {
+        if (hi) return euler ? launch_trace(lit::trace_kernel<0, QUEUE, true>, QUEUE, p, cfg, stream)
+                             : launch_trace(lit::trace_kernel<1, QUEUE, true>, QUEUE, p, cfg, stream);
+        return euler ? launch_trace(lit::trace_kernel<0, QUEUE, false>, QUEUE, p, cfg, stream)
+                     : launch_trace(lit::trace_kernel<1, QUEUE, false>, QUEUE, p, cfg, stream);
+    }
+    if (hi) return euler ? launch_trace(fus::trace_kernel<0, QUEUE, true>, QUEUE, p, cfg, stream)
+                         : launch_trace(fus::trace_kernel<1, QUEUE, true>, QUEUE, p, cfg, stream);
+    return euler ? launch_trace(fus::trace_kernel<0, QUEUE, false>, QUEUE, p, cfg, stream)
+                 : launch_trace(fus::trace_kernel<1, QUEUE, false>, QUEUE, p, cfg, stream);
 }
 
 cudaError_t launch_ray_pass(const PassParams &p, const LaunchConfig &cfg, cudaStream_t stream)
