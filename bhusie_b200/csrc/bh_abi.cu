@@ -420,11 +420,23 @@ int bh_ray_pipeline_pass_to_host(bh_ray_pipeline *p, const bh_camera_uniform *ca
     if (rc != BH_OK) return rc;
     if (!pinned_host_rgba32f) { set_error("bh_ray_pipeline_pass_to_host: host buffer is NULL"); return BH_ERR_INVALID; }
     if (p->bound_frame) { set_error("bh_ray_pipeline_pass_to_host: output is bound to an external frame (bh_ray_pipeline_bind_frame)"); return BH_ERR_STATE; }
-    if (n_chunks == 0) n_chunks = 1;
     if (n_chunks > 16) n_chunks = 16;
     bh_ctx *c = p->ctx;
     BH_CUDA(cudaSetDevice(c->device));
     cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    if (n_chunks == 0) {
+        // zero-copy: the kernel's 16-byte pixel stores go straight to the caller's page-locked buffer over PCIe while it
+        // is still tracing (a 4K frame is 133 MB per ~20 ms = 6.5 GB/s, a fraction of the link), so there is no D2H step
+        void *mapped = nullptr;
+        cudaError_t e = cudaHostGetDevicePointer(&mapped, pinned_host_rgba32f, 0);
+        if (e != cudaSuccess) { cudaGetLastError(); set_error("bh_ray_pipeline_pass_to_host: n_chunks=0 needs page-locked, mapped host memory (%s)", cudaGetErrorString(e)); return BH_ERR_INVALID; }
+        P.out = static_cast<float4 *>(mapped);
+        LaunchConfig cfg0{ c->sm_count, c->numeric_mode };
+        p->last_stream = stream; p->ran = true;
+        if (p->local_rows == 0) return BH_OK;
+        BH_CUDA(launch_ray_pass(P, cfg0, stream));
+        return BH_OK;
+    }
     if (!p->copy_stream) {
         BH_CUDA(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
         for (auto &e : p->chunk_done) BH_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));

@@ -169,7 +169,9 @@ int  bh_ray_pipeline_pass(bh_ray_pipeline *p, const bh_camera_uniform *camera,
 /* pass + read-back in one call for callers whose consumer lives on the host side of the bus (the reference's wgpu
  * post chain): same as bh_ray_pipeline_pass, then the RGBA32F output is copied to `pinned_host_rgba32f`
  * (local_rows*width*16 B of page-locked memory).  On the base level the frame is traced as n_chunks (1..16) row bands and
- * each band's D2H copy overlaps the tracing of the next.  Asynchronous; bh_ray_pipeline_sync() waits for kernels and copies. */
+ * each band's D2H copy overlaps the tracing of the next.  n_chunks == 0 selects ZERO-COPY: the kernel stores finished pixels
+ * directly into the (mapped) page-locked buffer over PCIe while it traces, so no copy is enqueued at all (the pipeline's
+ * own device buffer is not written by that pass).  Asynchronous; bh_ray_pipeline_sync() waits for kernels and copies. */
 int  bh_ray_pipeline_pass_to_host(bh_ray_pipeline *p, const bh_camera_uniform *camera,
                                   const bh_black_hole_uniform *black_hole, const bh_ray_details *details,
                                   float *pinned_host_rgba32f, uint32_t n_chunks, void *cuda_stream);

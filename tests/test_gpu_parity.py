@@ -357,7 +357,7 @@ def test_pass_to_host_chunked(ctx_small):
     """bh_ray_pipeline_pass_to_host: chunk-overlapped read-back gives the same bytes and statistics as pass + read."""
     import torch
     cam, hole, det = U.Camera(), U.BlackHole(), U.RayDetails(integration_method=1, model_count=1)
-    for (w, h, chunks) in ((120, 67, 8), (64, 9, 16), (33, 40, 3), (16, 4, 5)):
+    for (w, h, chunks) in ((120, 67, 8), (64, 9, 16), (33, 40, 3), (16, 4, 5), (120, 67, 0), (33, 40, 0)):   # 0 = zero-copy stores
         rp, ref, st = render(ctx_small, w, h, cam, hole, det, aux=0)
         host = torch.zeros((h, w, 4), dtype=torch.float32).pin_memory()
         rp.pass_to_host(cam, hole, det, host.data_ptr(), chunks)
