@@ -13,7 +13,8 @@ ray.wgsl:528); fps = 1000 / ms_per_step is reported beside it.
   value      whole-job ray-steps/s with the scene resident in HBM (device-timed, max over ranks)
   e2e        same metric through the public API with HOST buffers: per step the ModelUniform blob
              (48 MB — the reference re-sends it every frame, array_buffer.rs:71-79) goes H2D from
-             pinned memory, the pass runs, and the RGBA32F frame comes back D2H
+             pinned memory, the pass runs, and the RGBA32F frame lands in pinned host memory (zero-copy stores over PCIe
+             while the kernel traces; --e2e-chunks k for banded cudaMemcpyAsync instead)
   roofline   HBM bound per BASELINE.md §4: algorithmic bytes (256 B per ray-step + ...) / kernel time
   cpu_baseline / --impl reference: the CPU restatement of the reference pass (oracle, strict libm
              flavour, OpenMP on all host cores) on a bounded sample of the same workload.  The
@@ -321,7 +322,9 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pinned_model.numel() + 196),
                     "d2h_bytes_per_step": int(W * H * 16), "ms_per_step": 1000.0 * e2e_s / args.steps, "fps": args.steps / e2e_s,
                     "frame_checksum": checksum,
-                    "path": (f"bh_ctx_upload_models_async + bh_ray_pipeline_pass_to_host({args.e2e_chunks} bands, D2H overlapped) + sync"
+                    "path": ("bh_ctx_upload_models_async + bh_ray_pipeline_pass_to_host("
+                             + ("zero-copy: pixel stores land in the pinned host frame over PCIe during the pass" if args.e2e_chunks == 0
+                                else f"{args.e2e_chunks} bands, D2H overlapped") + ") + sync"
                              if world == 1 else f"upload_models_async + tiled pass ({frame.exchange} exchange) + D2H of the assembled frame")},
             "gpu_launches": int(args.steps * 1),
             "clocks": clocks,
@@ -370,7 +373,9 @@ def main():
     ap.add_argument("--height", type=int, default=2160)
     ap.add_argument("--band-rows", type=int, default=8)
     ap.add_argument("--numeric-mode", default="fused", choices=["fused", "literal"])
-    ap.add_argument("--e2e-chunks", type=int, default=8)
+    ap.add_argument("--e2e-chunks", type=int, default=0,
+                    help="N=1 e2e read-back: 0 = zero-copy (kernel stores pixels into the pinned host frame over PCIe while tracing), "
+                         "k>0 = k row bands with overlapped cudaMemcpyAsync")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: p2p = kernels store straight into rank 0's frame over NVLink (CUDA IPC); nccl = gather of band buffers")
     ap.add_argument("--no-cpu-baseline", action="store_true")
