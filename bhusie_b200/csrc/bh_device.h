@@ -52,6 +52,7 @@ struct PassParams {
     unsigned int n_items;            // tile mode: items [item_begin, n_items) are 8x4 warp tiles of this launch
     unsigned int item_begin;
     int tiles_x;
+    float disk_k;                    // 1.0021 * |hole.normal| (+inf when degenerate): fast disk-plane rejection, ray_impl.cuh hot_iteration
 };
 
 struct SkyParams {
