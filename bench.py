@@ -292,17 +292,18 @@ def run_ours(args):
         abytes = algorithmic_bytes(local, n_px_local)
         achieved = abytes / (kernel_ms * 1e-3) / 1e9
         traffic = None
-        inst_per_step = None
-        # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel on this workload
+        pj = {}
+        # dram__bytes_read.sum + dram__bytes_write.sum, warp instructions, FMA-pipe units and register operand reads per
+        # warp-step: one `ncu --set full` capture of this kernel on this workload (profiles/trace_kernel_dram.json)
         prof = os.path.join(ROOT, "profiles", "trace_kernel_dram.json")
         if os.path.exists(prof) and (W, H) == (3840, 2160) and world == 1:
             try:
                 with open(prof) as f:
                     pj = json.load(f).get(args.numeric_mode, {})
                 traffic = pj.get("dram_bytes_per_launch")
-                inst_per_step = pj.get("warp_inst_per_warp_step")
             except Exception:
-                traffic = None
+                traffic, pj = None, {}
+        inst_per_step = pj.get("warp_inst_per_warp_step")
         fp32_peak_tflops = 148 * 128 * 2 * (peak_json.get("sm_max_mhz", 1965.0) * 1e6) / 1e12
         flops = 400.0 * local["ray_steps"]
         line = {
@@ -329,23 +330,36 @@ def run_ours(args):
             "gpu_launches": int(args.steps * 1),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "kernel": "trace_kernel<1,false>", "kernel_ms": kernel_ms,
+                         "peak_source": peak_src, "kernel": "trace_kernel<1,false,4,origin>", "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": abytes,
                          "note": "ray state is register-resident: algorithmic bytes (256 B/ray-step, SURVEY §8d) are not DRAM traffic; "
-                                 "frac > 1 means the kernel beats the streamed-state HBM formulation, see roofline_fp32 for the binding limit"},
+                                 "frac > 1 means the kernel beats the streamed-state HBM formulation; roofline_issue / roofline_fma_pipe / roofline_regfile are the limits it runs against"},
             "roofline_fp32": {"bound": "fp32-alu", "achieved": flops / (kernel_ms * 1e-3) / 1e12, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
                               "frac": flops / (kernel_ms * 1e-3) / 1e12 / fp32_peak_tflops, "flops_per_ray_step": 400,
                               "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz (non-tensor FP32, BASELINE.md §2)"},
         }
         if inst_per_step:
-            # the binding limit: warp-instruction issue (1 per SMSP per clock).  Instructions per warp-ray-step come from the
-            # committed ncu capture of this kernel (profiles/trace_kernel_dram.json); time and clock are measured live.
-            sm_clock_hz = (clocks or {}).get("sm_mhz") or peak_json.get("sm_max_mhz", 1965.0)
-            issue_peak = 148 * 4 * sm_clock_hz * 1e6
-            issued = inst_per_step * (local["ray_steps"] / 32.0) / (kernel_ms * 1e-3)
-            line["roofline_issue"] = {"bound": "warp-instruction issue", "achieved": issued / 1e9, "peak": issue_peak / 1e9,
-                                      "unit": "G warp-inst/s", "frac": issued / issue_peak, "warp_inst_per_warp_ray_step": inst_per_step,
+            # The three limits the hot loop actually runs against, all per SM sub-partition and clock: one warp instruction
+            # issued, one FMA-pipe unit (a packed FFMA2/FMUL2/FADD2 is two), two 32-bit register operands per lane read
+            # (tools/ubench/fma_pipe.cu measures the last two).  Per-warp-step counts come from the committed ncu capture of
+            # this kernel (profiles/trace_kernel_dram.json); time and clock are measured live.
+            sm_clock_hz = ((clocks or {}).get("sm_mhz") or peak_json.get("sm_max_mhz", 1965.0)) * 1e6
+            slots = 148 * 4 * sm_clock_hz
+            warp_steps_per_s = (local["ray_steps"] / 32.0) / (kernel_ms * 1e-3)
+            line["roofline_issue"] = {"bound": "warp-instruction issue", "achieved": inst_per_step * warp_steps_per_s / 1e9, "peak": slots / 1e9,
+                                      "unit": "G warp-inst/s", "frac": inst_per_step * warp_steps_per_s / slots,
+                                      "warp_inst_per_warp_ray_step": inst_per_step,
                                       "peak_source": "148 SM x 4 schedulers x SM clock sampled during the run"}
+            if pj.get("fma_pipe_units_per_warp_step"):
+                u = pj["fma_pipe_units_per_warp_step"]
+                line["roofline_fma_pipe"] = {"bound": "FP32 FMA pipe", "achieved": u * warp_steps_per_s / 1e9, "peak": slots / 1e9,
+                                             "unit": "G pipe-units/s", "frac": u * warp_steps_per_s / slots, "units_per_warp_ray_step": u,
+                                             "peak_source": "1 scalar FP32 warp instruction (or half a packed one) per sub-partition per clock"}
+            if pj.get("reg_operand_reads_per_warp_step"):
+                r = pj["reg_operand_reads_per_warp_step"]
+                line["roofline_regfile"] = {"bound": "register-file operand bandwidth", "achieved": r * warp_steps_per_s / 1e9, "peak": 2 * slots / 1e9,
+                                            "unit": "G operand reads/s", "frac": r * warp_steps_per_s / (2 * slots), "reads_per_warp_ray_step": r,
+                                            "peak_source": "2 x 32-bit register source operands per lane per clock per sub-partition (measured)"}
         # CPU baseline beside it (N=1 only): bounded sample of the same workload
         if world == 1 and not args.no_cpu_baseline:
             try:

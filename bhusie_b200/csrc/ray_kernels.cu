@@ -19,6 +19,7 @@
 #include "bh_device.h"
 #include "detmath.cuh"
 #include <cuda_fp16.h>
+#include <string.h>
 
 namespace bh {
 
@@ -57,6 +58,26 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 constexpr int kTopNodes = 256;
 constexpr int kTopHeaderBytes = 64;                       // 48 used, padded to keep the nodes 16-byte aligned
 constexpr int kTopBytes = kTopHeaderBytes + kTopNodes * 32;
+
+// Resident CTAs per SM (tuning: -DBH_OCC_RK=n -DBH_OCC_EULER=n).  Measured at 4K (tools/gpu_time_modes.py): the Cash-Karp
+// kernel is fastest spill-free at 4 CTAs/SM (14.9 ms; 5: 15.1, 6: 15.3 — its hot loop runs at the register-operand
+// bandwidth of the SM, so more warps buy nothing); Euler gains 4 % at 5 CTAs/SM on frames that saturate the GPU.
+#ifndef BH_OCC_RK
+#define BH_OCC_RK 4
+#endif
+#ifndef BH_OCC_EULER
+#define BH_OCC_EULER 5
+#endif
+#ifndef BH_OCC_PAIR
+#define BH_OCC_PAIR 4
+#endif
+// 1: FUSED mode runs the experimental two-rays-per-thread kernel (ray_pair.cuh: bit-identical, same speed); 0: one ray per thread
+#ifndef BH_USE_PAIR
+#define BH_USE_PAIR 0
+#endif
+#ifndef BH_PAIR_UNROLL
+#define BH_PAIR_UNROLL 0
+#endif
 
 #define BH_NUM_NS lit
 #define BH_FUSED 0
@@ -161,15 +182,14 @@ __global__ void math_probe_kernel(int fn, const float *a, const float *b, float 
 // launchers
 // ------------------------------------------------------------------------------------------------
 template <typename K>
-static cudaError_t launch_trace(K kernel, bool queue, const PassParams &p, const LaunchConfig &cfg, cudaStream_t stream)
+static cudaError_t launch_trace(K kernel, unsigned items, const PassParams &p, const LaunchConfig &cfg, cudaStream_t stream)
 {
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, 0);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     unsigned grid = (unsigned)(cfg.sm_count * per_sm);      // persistent: one wave of resident CTAs
-    // never more CTAs than there can be work: tile mode knows the item count, queue mode its upper bound
-    const unsigned items = queue ? (unsigned)(((size_t)p.local_rows * (size_t)p.w + 31) / 32) : p.n_items - p.item_begin;
+    // never more CTAs than there can be work (`items` = warp work items of this launch, an upper bound in queue mode)
     const unsigned need = (items + 3u) / 4u;
     if (need < grid) grid = need ? need : 1u;
     kernel<<<grid, 128, 0, stream>>>(p);
@@ -180,19 +200,39 @@ template <bool QUEUE>
 static cudaError_t launch_trace_mode(const PassParams &p, const LaunchConfig &cfg, cudaStream_t stream)
 {
     const bool euler = p.det.integration_method == 0;
-    // high-occupancy build only when every warp of it would still get several items (tile mode knows the count)
-    const unsigned warps_hi = (unsigned)cfg.sm_count * 4u * (euler ? 8u : 5u);
-    const bool hi = !QUEUE && (p.n_items - p.item_begin) >= 6u * warps_hi;
+    // warp work items: 8x4 tiles (tile mode) / 32 queue entries
+    const unsigned items = QUEUE ? (unsigned)(((size_t)p.local_rows * (size_t)p.w + 31) / 32) : p.n_items - p.item_begin;
+    // Euler only: the higher-occupancy build when every warp of it would still get several items (tile mode knows the count)
+    const bool hi = !QUEUE && euler && BH_OCC_EULER != 4 && items >= 6u * (unsigned)cfg.sm_count * 4u * (unsigned)BH_OCC_EULER;
     if (cfg.numeric_mode == BH_NUMERIC_LITERAL) {
-        if (hi) return euler ? launch_trace(lit::trace_kernel<0, QUEUE, true>, QUEUE, p, cfg, stream)
-                             : launch_trace(lit::trace_kernel<1, QUEUE, true>, QUEUE, p, cfg, stream);
-        return euler ? launch_trace(lit::trace_kernel<0, QUEUE, false>, QUEUE, p, cfg, stream)
-                     : launch_trace(lit::trace_kernel<1, QUEUE, false>, QUEUE, p, cfg, stream);
+        if (!euler) return launch_trace(lit::trace_kernel<1, QUEUE, 4, false>, items, p, cfg, stream);
+        if (!QUEUE && hi) return launch_trace(lit::trace_kernel<0, false, BH_OCC_EULER, false>, items, p, cfg, stream);
+        return launch_trace(lit::trace_kernel<0, QUEUE, 4, false>, items, p, cfg, stream);
     }
-    if (hi) return euler ? launch_trace(fus::trace_kernel<0, QUEUE, true>, QUEUE, p, cfg, stream)
-                         : launch_trace(fus::trace_kernel<1, QUEUE, true>, QUEUE, p, cfg, stream);
-    return euler ? launch_trace(fus::trace_kernel<0, QUEUE, false>, QUEUE, p, cfg, stream)
-                 : launch_trace(fus::trace_kernel<1, QUEUE, false>, QUEUE, p, cfg, stream);
+    // hole at exactly (+0,+0,+0) (bit pattern 0 in all three words; the reference's default): the build without the
+    // `- bh.position` subtractions, which are bit-for-bit no-ops there
+    unsigned pos_bits[3];
+    memcpy(pos_bits, p.hole.position, sizeof pos_bits);
+    const bool origin = (pos_bits[0] | pos_bits[1] | pos_bits[2]) == 0u;
+#if BH_USE_PAIR
+    {   // two rays per thread: a warp item is an 8x8 tile (two tile rows) / 64 queue entries
+        const unsigned tile_rows = QUEUE ? 0u : (p.n_items - p.item_begin) / (unsigned)p.tiles_x;
+        const unsigned pair_items = QUEUE ? (items + 1u) / 2u : ((tile_rows + 1u) / 2u) * (unsigned)p.tiles_x;
+        if (origin) return euler ? launch_trace(fus::trace_pair_kernel<0, QUEUE, true>, pair_items, p, cfg, stream)
+                                 : launch_trace(fus::trace_pair_kernel<1, QUEUE, true>, pair_items, p, cfg, stream);
+        return euler ? launch_trace(fus::trace_pair_kernel<0, QUEUE, false>, pair_items, p, cfg, stream)
+                     : launch_trace(fus::trace_pair_kernel<1, QUEUE, false>, pair_items, p, cfg, stream);
+    }
+#else
+    if (origin) {
+        if (!euler) return launch_trace(fus::trace_kernel<1, QUEUE, BH_OCC_RK, true>, items, p, cfg, stream);
+        if (!QUEUE && hi) return launch_trace(fus::trace_kernel<0, false, BH_OCC_EULER, true>, items, p, cfg, stream);
+        return launch_trace(fus::trace_kernel<0, QUEUE, 4, true>, items, p, cfg, stream);
+    }
+    if (!euler) return launch_trace(fus::trace_kernel<1, QUEUE, BH_OCC_RK, false>, items, p, cfg, stream);
+    if (!QUEUE && hi) return launch_trace(fus::trace_kernel<0, false, BH_OCC_EULER, false>, items, p, cfg, stream);
+    return launch_trace(fus::trace_kernel<0, QUEUE, 4, false>, items, p, cfg, stream);
+#endif
 }
 
 cudaError_t launch_ray_pass(const PassParams &p, const LaunchConfig &cfg, cudaStream_t stream)

@@ -15,7 +15,10 @@ def main():
     tex, src = assets.load_textures()
     blob, info = P.load_obj_model(assets.lucy_path()) if assets.have_lucy() else P.model_from_arrays(*assets.uv_sphere())
     res = {}
-    for mode, name in ((P.NUMERIC_LITERAL, "literal"), (P.NUMERIC_FUSED, "fused")):
+    modes = ((P.NUMERIC_LITERAL, "literal"), (P.NUMERIC_FUSED, "fused"))
+    if os.environ.get("BH_TIME_FUSED_ONLY"):
+        modes = modes[1:]
+    for mode, name in modes:
         ctx = P.Context(0, numeric_mode=mode)
         ctx.set_textures(tex)
         ctx.upload_models(blob)
@@ -39,7 +42,7 @@ def main():
             rp.close()
         ctx.close()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "time_modes.json"), "w"), indent=1)
+    json.dump(res, open(os.path.join(ROOT, "gpurun_out", os.environ.get("BH_TIME_OUT", "time_modes.json")), "w"), indent=1)
 
 
 if __name__ == "__main__":
