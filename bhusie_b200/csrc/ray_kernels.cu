@@ -60,13 +60,15 @@ constexpr int kTopHeaderBytes = 64;                       // 48 used, padded to 
 constexpr int kTopBytes = kTopHeaderBytes + kTopNodes * 32;
 
 // Resident CTAs per SM (tuning: -DBH_OCC_RK=n -DBH_OCC_EULER=n).  Measured at 4K (tools/gpu_time_modes.py): the Cash-Karp
-// kernel is fastest spill-free at 4 CTAs/SM (14.9 ms; 5: 15.1, 6: 15.3 — its hot loop runs at the register-operand
-// bandwidth of the SM, so more warps buy nothing); Euler gains 4 % at 5 CTAs/SM on frames that saturate the GPU.
+// kernel is fastest spill-free at 4 CTAs/SM (14.7 ms; 5: 15.1, 6: 15.3): its hot loop runs at ~70 % of three coincident
+// limits (issue slots, FMA pipe, register operand bandwidth), so extra warps buy nothing once spills appear.  Euler is flat
+// from 4 to 6 (8.61 / 8.58 / 8.62 ms) and loses at 8 (9.36 ms, spills).  A value other than 4 for Euler adds a second build
+// that launch_trace_mode uses on frames that saturate the GPU.
 #ifndef BH_OCC_RK
 #define BH_OCC_RK 4
 #endif
 #ifndef BH_OCC_EULER
-#define BH_OCC_EULER 5
+#define BH_OCC_EULER 4
 #endif
 #ifndef BH_OCC_PAIR
 #define BH_OCC_PAIR 4

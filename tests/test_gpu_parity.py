@@ -8,6 +8,8 @@ Gates:
 """
 import ctypes as C
 
+import struct
+
 import numpy as np
 import pytest
 
@@ -200,6 +202,48 @@ def test_random_scenes_bit_exact(ctx_small, oracle, small_oracle_scene):
         finally:
             ctx_small.set_model_header(0, (-10.0, 0.0, 30.0), 1)
     assert n_hit > 0
+
+
+class _HoleWithNormal(U.BlackHole):
+    """BlackHole whose uniform carries an arbitrary `normal` (bytes 32..44): the ABI takes the bytes verbatim, and the hot
+    loop's fast disk-plane rejection is derived from that vector (PassParams.disk_k)."""
+    normal_override = None
+
+    def uniform(self) -> bytes:
+        b = bytearray(super().uniform())
+        if self.normal_override is not None:
+            b[32:44] = struct.pack("<3f", *self.normal_override)
+        return bytes(b)
+
+
+@pytest.mark.parametrize("case", ["zero_normal", "tiny_normal", "scaled_normal", "tiny_step", "radial_rk", "radial_euler", "grazing_plane"])
+def test_hot_loop_fallbacks_bit_exact(ctx_small, oracle, small_oracle_scene, case):
+    """The hot loop runs every step speculatively (unguarded sqrt/rcp, provable-miss tests for horizon and disk) and
+    falls back to the literal per-step code when a test fails; these scenes sit on the fallbacks: degenerate or
+    non-unit disk normals, steps far below the horizon margin, rays with zero angular momentum (|p x d| == 0, the
+    sqrt operand is exactly 0), and a camera inside the disk plane (every step within one step of the plane)."""
+    cam, hole, det = U.Camera(), _HoleWithNormal(), U.RayDetails(integration_method=1, model_count=1)
+    w, h = 45, 27
+    if case == "zero_normal": hole.normal_override = (0.0, 0.0, 0.0)
+    if case == "tiny_normal": hole.normal_override = (1e-20, -2e-20, 5e-21)
+    if case == "scaled_normal":
+        n = hole.frame()[1]
+        hole.normal_override = tuple(float(3.0 * c) for c in n)
+    if case == "tiny_step":
+        cam = U.Camera(position=(3, 1, -6))
+        det = U.RayDetails(integration_method=1, model_count=1, step_size=2e-4, max_iterations=400)
+    if case in ("radial_rk", "radial_euler"):
+        cam = U.Camera(position=(0, 0, -8))
+        det = U.RayDetails(integration_method=1 if case == "radial_rk" else 0, model_count=0)
+        w, h = 33, 17                                   # odd: the centre pixel looks straight at the hole
+    if case == "grazing_plane":
+        hole = _HoleWithNormal(accretion_disk_rotation=(0.0, 0.0, 0.0))      # disk plane y = 0, camera in it
+        cam = U.Camera(position=(0, 0, -19))
+    rp, dev, st = render(ctx_small, w, h, cam, hole, det)
+    ora = oracle.ray_pass(small_oracle_scene, w, h, cam.uniform(), hole.uniform(), det.uniform(), flavour=fl(ctx_small))
+    assert_bit_exact(dev, ora, case)
+    assert_stats(st, ora.counters)
+    rp.close()
 
 
 def test_ragged_sizes_bit_exact(ctx_small, oracle, small_oracle_scene):
