@@ -70,6 +70,10 @@ constexpr int kTopBytes = kTopHeaderBytes + kTopNodes * 32;
 #ifndef BH_OCC_EULER
 #define BH_OCC_EULER 4
 #endif
+// lanes of a warp that must wait for disk shading before the hot phase is interrupted for them (1 = serve every crossing at once)
+#ifndef BH_SHADE_BATCH
+#define BH_SHADE_BATCH 8
+#endif
 #ifndef BH_OCC_PAIR
 #define BH_OCC_PAIR 4
 #endif
