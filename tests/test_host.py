@@ -163,3 +163,17 @@ def test_bench_accounting():
     assert bench.algorithmic_bytes(st, 100) == 256 * 1000 + 16 * 100 + 64 * 10 + 124 * 5 + 16 * 7
     peak, src, _ = bench.peaks()
     assert peak > 1000 and ("measured" in src or "fallback" in src)
+
+
+def test_rust_shim_declares_every_abi_symbol():
+    """rust_shim/  cannot be compiled here (no Rust toolchain); at least keep its raw bindings in step with
+    the header: every function include/bh_abi.h declares appears as `pub fn <name>(` in rust_shim/src/ffi.rs, and nothing else."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "bh_abi.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(bh_[a-z0-9_]+)\s*\(", header))
+    rust = open(os.path.join(root, "rust_shim", "src", "ffi.rs")).read()
+    bound = set(re.findall(r"pub fn (bh_[a-z0-9_]+)\s*\(", rust))
+    assert declared == bound, (sorted(declared - bound), sorted(bound - declared))
+    assert declared == set(_lib.SYMBOLS)
