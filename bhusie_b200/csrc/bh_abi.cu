@@ -349,6 +349,7 @@ static int build_pass_params(bh_ray_pipeline *p, const bh_camera_uniform *camera
     P.aux_hit = p->aux_hit; P.aux_steps = p->aux_steps; P.aux_class = p->aux_class;
     P.stats = p->stats; P.work = p->work; P.queue = p->queue;
     P.tiles_x = (int)((p->w + 7) / 8);
+    P.tile_rows = 4;
     P.item_begin = 0;
     P.n_items = (unsigned)P.tiles_x * (unsigned)((p->local_rows + 3) / 4);
     {   // conservative bound used only to SKIP a test whose outcome is then provably "miss" (any value >= 1.001 |n| is valid)

@@ -52,6 +52,7 @@ struct PassParams {
     unsigned int n_items;            // tile mode: items [item_begin, n_items) are 8x4 warp tiles of this launch
     unsigned int item_begin;
     int tiles_x;
+    unsigned int tile_rows;          // rows of a tile-mode work item: 4 (8x4 pixels, 32 rays per warp), or 2 / 1 on launches that do not fill the GPU
     float disk_k;                    // 1.0021 * |hole.normal| (+inf when degenerate): fast disk-plane rejection, ray_impl.cuh hot_iteration
 };
 

@@ -207,9 +207,23 @@ static cudaError_t launch_trace_mode(const PassParams &p, const LaunchConfig &cf
 {
     const bool euler = p.det.integration_method == 0;
     // warp work items: 8x4 tiles (tile mode) / 32 queue entries
-    const unsigned items = QUEUE ? (unsigned)(((size_t)p.local_rows * (size_t)p.w + 31) / 32) : p.n_items - p.item_begin;
+    // (queue mode: an upper bound, in the narrowest items trace_kernel may choose, so that the grid is not what limits it)
+    const unsigned items = QUEUE ? (unsigned)(((size_t)p.local_rows * (size_t)p.w + 7) / 8) : p.n_items - p.item_begin;
     // Euler only: the higher-occupancy build when every warp of it would still get several items (tile mode knows the count)
     const bool hi = !QUEUE && euler && BH_OCC_EULER != 4 && items >= 6u * (unsigned)cfg.sm_count * 4u * (unsigned)BH_OCC_EULER;
+    if (!QUEUE && p.tile_rows == 4 && p.item_begin == 0 && p.n_items == (unsigned)p.tiles_x * (unsigned)((p.local_rows + 3) / 4)) {
+        // whole-frame tile launch with fewer 8x4 tiles than warp slots: 8x2 or 8x1 tiles (see trace_kernel)
+        const unsigned slots = (unsigned)cfg.sm_count * 4u * 4u;
+        for (unsigned r = 1; r <= 2; r *= 2) {
+            const unsigned n = (unsigned)p.tiles_x * (unsigned)((p.local_rows + (int)r - 1) / (int)r);
+            if (n <= slots) {
+                PassParams q = p;
+                q.tile_rows = r;
+                q.n_items = n;
+                return launch_trace_mode<QUEUE>(q, cfg, stream);
+            }
+        }
+    }
     if (cfg.numeric_mode == BH_NUMERIC_LITERAL) {
         if (!euler) return launch_trace(lit::trace_kernel<1, QUEUE, 4, false>, items, p, cfg, stream);
         if (!QUEUE && hi) return launch_trace(lit::trace_kernel<0, false, BH_OCC_EULER, false>, items, p, cfg, stream);
