@@ -6,12 +6,15 @@
 //   * classify_kernel (fine pyramid levels only) decides copy / interpolate / trace per pixel
 //     (ray.wgsl:185-241), writes the first two directly and appends the third to a device queue
 //     with one warp-ballot-compacted atomic per warp.
-//   * trace_kernel is a persistent grid (k CTAs per SM); each WARP pulls work items — an 8x4
-//     pixel tile on the base level, 32 queue entries on fine levels — from a global counter.
-//     Ray state (32 scalars) lives in registers for the whole ray.  The per-ray state machine of
-//     trace_ray (ray.wgsl:482-596) is run phase-sorted inside the warp: all lanes that want an
-//     integration step run the hot loop together; lanes that left the relativity sphere wait and
-//     are then served together by the flat-space branch (BVH + sphere re-entry).  Every ray still
+//   * trace_kernel is a persistent grid (4 CTAs per SM); each WARP pulls work items — an 8x4
+//     pixel tile on the base level, 32 queue entries on fine levels (fewer rays per warp on launches
+//     that do not fill the GPU) — from a global counter.  A ray's integrator state (9 scalars) lives in
+//     registers; the other variables of trace_ray (ray.wgsl:482-596) live in a per-thread row of
+//     shared memory and are only written when something happens to the ray.  The per-ray state
+//     machine is run phase-sorted inside the warp: all lanes that want an integration step run the
+//     hot loop together (one basic block per step, hot_iteration in ray_impl.cuh); lanes that
+//     crossed the disk are shaded together; lanes that left the relativity sphere wait and are
+//     then served together by the flat-space branch (BVH + sphere re-entry).  Every ray still
 //     executes exactly its own sequence of operations; only the interleaving across lanes differs.
 //
 // Numerics: compiled with --fmad=false, IEEE div/sqrt; one float op per WGSL expression node,
