@@ -177,3 +177,22 @@ def test_rust_shim_declares_every_abi_symbol():
     bound = set(re.findall(r"pub fn (bh_[a-z0-9_]+)\s*\(", rust))
     assert declared == bound, (sorted(declared - bound), sorted(bound - declared))
     assert declared == set(_lib.SYMBOLS)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` is a CPU arm (the oracle's strict flavour with OpenMP on a bounded sample): it must run
+    without a GPU and print ONE JSON line with the contract's keys, its own value echoed in cpu_baseline and e2e."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip().startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "Mray-steps/sec" and d["unit"] == "Mray-steps/s" and d["higher_is_better"] is True
+    assert d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
