@@ -214,7 +214,8 @@ static cudaError_t launch_trace_mode(const PassParams &p, const LaunchConfig &cf
     const unsigned items = QUEUE ? (unsigned)(((size_t)p.local_rows * (size_t)p.w + 7) / 8) : p.n_items - p.item_begin;
     // Euler only: the higher-occupancy build when every warp of it would still get several items (tile mode knows the count)
     const bool hi = !QUEUE && euler && BH_OCC_EULER != 4 && items >= 6u * (unsigned)cfg.sm_count * 4u * (unsigned)BH_OCC_EULER;
-    if (!QUEUE && p.tile_rows == 4 && p.item_begin == 0 && p.n_items == (unsigned)p.tiles_x * (unsigned)((p.local_rows + 3) / 4)) {
+    // (the experimental two-rays-per-thread kernel keeps its 8x8 items)
+    if (!BH_USE_PAIR && !QUEUE && p.tile_rows == 4 && p.item_begin == 0 && p.n_items == (unsigned)p.tiles_x * (unsigned)((p.local_rows + 3) / 4)) {
         // whole-frame tile launch with fewer 8x4 tiles than warp slots: 8x2 or 8x1 tiles (see trace_kernel)
         const unsigned slots = (unsigned)cfg.sm_count * 4u * 4u;
         for (unsigned r = 1; r <= 2; r *= 2) {
