@@ -1,6 +1,6 @@
 """Builds libbhray.so (the C-ABI library: CUDA kernels + host code) in-tree with nvcc for sm_100a.
 
-    python -m bhusie_b200.build [--force] [--verbose]
+    python -m bhusie_b200.build [--force] [--verbose] [--pair]
 
 Flags that matter for parity: --fmad=false (no implicit FMA contraction),
 IEEE division and square root (nvcc defaults -prec-div=true -prec-sqrt=true; no -use_fast_math).
@@ -63,4 +63,10 @@ def build_library(force: bool = False, verbose: bool = False, extra: list[str] |
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    if "--pair" in sys.argv:
+        # the experimental two-rays-per-thread kernel (csrc/ray_pair.cuh) as a second library; run anything against it
+        # with BHRAY_LIB=bhusie_b200/lib/libbhray_pair.so (e.g. the whole `pytest -m gpu` suite: it is bit-identical)
+        print(build_library(force=True, verbose="--verbose" in sys.argv, extra=["-DBH_USE_PAIR=1"],
+                            out=os.path.join(LIB_DIR, "libbhray_pair.so")))
+    else:
+        print(build_library(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
