@@ -1,0 +1,88 @@
+"""The product's device source on the CPU, against the oracle — no GPU needed.
+
+tests/host_kernel/host_kernel.cpp compiles bhusie_b200/csrc/ray_impl.cuh + detmath.cuh with g++ (one lane per "warp",
+warp votes / atomics / packed-FP32 intrinsics emulated one IEEE operation each) and runs trace_warp pixel by pixel.  What
+this pins without a GPU is the LOGIC of the kernel's state machine — the speculative quiet step, the literal tail, the
+event / shading / flat-space phases, the cold rows — and its arithmetic as written, bit for bit against the oracle flavour
+of the numeric mode.  What it cannot see is anything ptxas or the hardware adds (contraction, MUFU seeds, scheduling): that
+is the job of the `-m gpu` suite, which runs the same comparisons through the C ABI on the real kernels.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, bits
+from bhusie_b200 import uniforms as U
+
+SRC = os.path.join(ROOT, "tests", "host_kernel", "host_kernel.cpp")
+OUT = os.path.join(ROOT, "tests", "host_kernel", "_build", "libbh_host_kernel.so")
+DEPS = [SRC] + [os.path.join(ROOT, "bhusie_b200", "csrc", f) for f in ("ray_impl.cuh", "detmath.cuh", "bh_device.h")]
+FLAVOUR = {0: "contract", 1: "fused"}
+STAT_NAMES = ("steps", "px_traced", "px_copied", "px_interp", "node_visits", "tri_tests", "tex_samples", "rk_reject", "stack_overflow")
+
+
+@pytest.fixture(scope="session")
+def host_kernel():
+    cuda_inc = "/usr/local/cuda/include"
+    if not os.path.isdir(cuda_inc):
+        pytest.skip("CUDA headers not found")
+    if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in DEPS):
+        os.makedirs(os.path.dirname(OUT), exist_ok=True)
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        cmd = [cxx, "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-march=x86-64-v3",
+               "-I", cuda_inc, "-x", "c++", SRC, "-o", OUT]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr[-4000:]
+    lib = C.CDLL(OUT)
+    lib.bh_host_kernel_pass.restype = C.c_int
+    return lib
+
+
+def host_pass(lib, mode, tex, blob, w, h, cam, hole, det):
+    rgba = np.zeros((h, w, 4), np.float32)
+    hit = np.zeros((h, w), np.int32)
+    steps = np.zeros((h, w), np.uint32)
+    stats = np.zeros(9, np.uint64)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    t = {k: np.ascontiguousarray(tex[k]) for k in ("color", "disk", "sky")}
+    rc = lib.bh_host_kernel_pass(C.c_int(mode), C.c_char_p(cam.uniform()), C.c_char_p(hole.uniform()), C.c_char_p(det.uniform()),
+                                 p(t["color"]), C.c_int(t["color"].shape[1]), C.c_int(t["color"].shape[0]),
+                                 p(t["disk"]), C.c_int(t["disk"].shape[1]), C.c_int(t["disk"].shape[0]),
+                                 p(t["sky"]), C.c_int(t["sky"].shape[1]), C.c_int(t["sky"].shape[0]),
+                                 p(blob), C.c_int(w), C.c_int(h), p(rgba), p(hit), p(steps), p(stats))
+    assert rc == 0
+    return rgba, hit, steps, dict(zip(STAT_NAMES, (int(x) for x in stats)))
+
+
+CASES = {
+    "default": (dict(), dict(), dict()),
+    "outside_sphere": (dict(position=(0, 0, -45)), dict(), dict()),
+    "oblique": (dict(position=(-28, 4, 24), forward=(0.6, -0.1, 0.2)), dict(), dict()),
+    "near_hole": (dict(position=(3, 1, -6)), dict(), dict()),
+    "moved_hole": (dict(), dict(position=(1.5, -0.5, 2.0)), dict()),
+    "big_step": (dict(), dict(), dict(step_size=0.8)),
+    "short": (dict(), dict(), dict(max_iterations=40)),
+    "tiny_step": (dict(position=(3, 1, -6)), dict(), dict(step_size=2e-4, max_iterations=400)),
+    "grazing_plane": (dict(), dict(accretion_disk_rotation=(0.0, 0.0, 0.0)), dict()),
+}
+
+
+@pytest.mark.parametrize("mode", [0, 1], ids=["literal", "fused"])
+@pytest.mark.parametrize("method", [0, 1], ids=["euler", "rk"])
+@pytest.mark.parametrize("case", list(CASES))
+def test_device_source_on_cpu_matches_oracle(host_kernel, oracle, small_scene, small_oracle_scene, mode, method, case):
+    tex, blob, _ = small_scene
+    ck, hk, dk = CASES[case]
+    cam, hole = U.Camera(**ck), U.BlackHole(**hk)
+    det = U.RayDetails(integration_method=method, model_count=1, time=1.25, **dk)
+    w, h = 33, 19                                     # odd: the centre pixel has zero angular momentum (sqrt operand exactly 0)
+    rgba, hit, steps, st = host_pass(host_kernel, mode, tex, blob, w, h, cam, hole, det)
+    ora = oracle.ray_pass(small_oracle_scene, w, h, cam.uniform(), hole.uniform(), det.uniform(), flavour=FLAVOUR[mode])
+    same = bits(rgba) == bits(ora.rgba)
+    assert same.all(), f"{case}: {(~same).mean():.3%} of RGBA words differ"
+    assert np.array_equal(hit, ora.hit) and np.array_equal(steps, ora.steps)
+    for k in ("steps", "px_traced", "node_visits", "tri_tests", "tex_samples", "rk_reject", "stack_overflow"):
+        assert st[k] == ora.counters[k], (k, st[k], ora.counters[k])
