@@ -69,7 +69,9 @@ static inline void mbar_wait(unsigned long long *, unsigned) {}
 constexpr int kTopNodes = 256;
 constexpr int kTopHeaderBytes = 64;
 constexpr int kTopBytes = kTopHeaderBytes + kTopNodes * 32;
-#define BH_USE_PAIR 0
+#ifndef BH_USE_PAIR
+#define BH_USE_PAIR 0          // -DBH_USE_PAIR=1: also the experimental two-rays-per-thread kernel (mode 2)
+#endif
 #define BH_SHADE_BATCH 8
 #define BH_NUM_NS lit
 #define BH_FUSED 0
@@ -115,6 +117,8 @@ extern "C" int bh_host_kernel_pass(int mode, const void *camera, const void *hol
     memcpy(pos_bits, P.hole.position, sizeof pos_bits);
     const bool origin = mode == 1 && (pos_bits[0] | pos_bits[1] | pos_bits[2]) == 0u;      // launch_trace_mode's choice
     const bool rk = P.det.integration_method != 0;
+    const bool origin2 = (pos_bits[0] | pos_bits[1] | pos_bits[2]) == 0u;
+    (void)origin2;
     unsigned long long steps_total = 0, traced = 0;
     for (int y = 0; y < h; ++y)
         for (int x = 0; x < w; ++x) {
@@ -127,6 +131,26 @@ extern "C" int bh_host_kernel_pass(int mode, const void *camera, const void *hol
                 if (P.det.model_count > 0) { memcpy(fus::s_model_top, models, 48); memcpy(fus::s_model_top + kTopHeaderBytes, models + kMuNodes, kTopNodes * 32); }
             }
             float4 rgba; int tri; unsigned steps;
+#if BH_USE_PAIR
+            if (mode == 2) {
+                // two-rays-per-thread kernel (FUSED): this pixel and its right-hand neighbour as the thread's pair
+                if (x & 1) continue;
+                const bool second = x + 1 < w;
+                fus::LaneOut o0, o1;
+                if (origin2) { if (rk) fus::trace_warp_pair<1, true>(P, true, x, y, second, x + 1, y, o0, o1); else fus::trace_warp_pair<0, true>(P, true, x, y, second, x + 1, y, o0, o1); }
+                else         { if (rk) fus::trace_warp_pair<1, false>(P, true, x, y, second, x + 1, y, o0, o1); else fus::trace_warp_pair<0, false>(P, true, x, y, second, x + 1, y, o0, o1); }
+                for (int k = 0; k < kStatCount; ++k) stats[k] += fus::s_warp_stats[0][k];
+                for (int r = 0; r < (second ? 2 : 1); ++r) {
+                    const fus::LaneOut &o = r ? o1 : o0;
+                    const size_t idx = (size_t)y * (size_t)w + (size_t)(x + r);
+                    memcpy(out_rgba + 4 * idx, &o.rgba, 16);
+                    if (out_hit) out_hit[idx] = o.tri;
+                    if (out_steps) out_steps[idx] = o.steps;
+                    steps_total += o.steps; ++traced;
+                }
+                continue;
+            }
+#endif
             if (mode == 0) {
                 const lit::LaneOut o = rk ? lit::trace_warp<1, false>(P, true, x, y) : lit::trace_warp<0, false>(P, true, x, y);
                 rgba = o.rgba; tri = o.tri; steps = o.steps;

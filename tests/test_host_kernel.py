@@ -19,26 +19,36 @@ from bhusie_b200 import uniforms as U
 
 SRC = os.path.join(ROOT, "tests", "host_kernel", "host_kernel.cpp")
 OUT = os.path.join(ROOT, "tests", "host_kernel", "_build", "libbh_host_kernel.so")
-DEPS = [SRC] + [os.path.join(ROOT, "bhusie_b200", "csrc", f) for f in ("ray_impl.cuh", "detmath.cuh", "bh_device.h")]
-FLAVOUR = {0: "contract", 1: "fused"}
+OUT_PAIR = os.path.join(ROOT, "tests", "host_kernel", "_build", "libbh_host_kernel_pair.so")
+DEPS = [SRC] + [os.path.join(ROOT, "bhusie_b200", "csrc", f) for f in ("ray_impl.cuh", "ray_pair.cuh", "detmath.cuh", "bh_device.h")]
+FLAVOUR = {0: "contract", 1: "fused", 2: "fused"}         # mode 2: the experimental two-rays-per-thread kernel (FUSED)
 STAT_NAMES = ("steps", "px_traced", "px_copied", "px_interp", "node_visits", "tri_tests", "tex_samples", "rk_reject", "stack_overflow")
+
+
+def _build(out, extra):
+    cuda_inc = "/usr/local/cuda/include"
+    if not os.path.isdir(cuda_inc):
+        pytest.skip("CUDA headers not found")
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in DEPS):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        cmd = [cxx, "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-march=x86-64-v3", *extra,
+               "-I", cuda_inc, "-x", "c++", SRC, "-o", out]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr[-4000:]
+    lib = C.CDLL(out)
+    lib.bh_host_kernel_pass.restype = C.c_int
+    return lib
 
 
 @pytest.fixture(scope="session")
 def host_kernel():
-    cuda_inc = "/usr/local/cuda/include"
-    if not os.path.isdir(cuda_inc):
-        pytest.skip("CUDA headers not found")
-    if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in DEPS):
-        os.makedirs(os.path.dirname(OUT), exist_ok=True)
-        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-        cmd = [cxx, "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-march=x86-64-v3",
-               "-I", cuda_inc, "-x", "c++", SRC, "-o", OUT]
-        res = subprocess.run(cmd, capture_output=True, text=True)
-        assert res.returncode == 0, res.stderr[-4000:]
-    lib = C.CDLL(OUT)
-    lib.bh_host_kernel_pass.restype = C.c_int
-    return lib
+    return _build(OUT, [])
+
+
+@pytest.fixture(scope="session")
+def host_kernel_pair():
+    return _build(OUT_PAIR, ["-DBH_USE_PAIR=1"])
 
 
 def host_pass(lib, mode, tex, blob, w, h, cam, hole, det):
@@ -81,6 +91,25 @@ def test_device_source_on_cpu_matches_oracle(host_kernel, oracle, small_scene, s
     w, h = 33, 19                                     # odd: the centre pixel has zero angular momentum (sqrt operand exactly 0)
     rgba, hit, steps, st = host_pass(host_kernel, mode, tex, blob, w, h, cam, hole, det)
     ora = oracle.ray_pass(small_oracle_scene, w, h, cam.uniform(), hole.uniform(), det.uniform(), flavour=FLAVOUR[mode])
+    same = bits(rgba) == bits(ora.rgba)
+    assert same.all(), f"{case}: {(~same).mean():.3%} of RGBA words differ"
+    assert np.array_equal(hit, ora.hit) and np.array_equal(steps, ora.steps)
+    for k in ("steps", "px_traced", "node_visits", "tri_tests", "tex_samples", "rk_reject", "stack_overflow"):
+        assert st[k] == ora.counters[k], (k, st[k], ora.counters[k])
+
+
+@pytest.mark.parametrize("method", [0, 1], ids=["euler", "rk"])
+@pytest.mark.parametrize("case", list(CASES))
+def test_two_ray_kernel_source_on_cpu_matches_oracle(host_kernel_pair, oracle, small_scene, small_oracle_scene, method, case):
+    """The experimental two-rays-per-thread kernel (csrc/ray_pair.cuh, not in the product library): horizontally adjacent
+    pixels as a thread's pair; same oracle, same bits."""
+    tex, blob, _ = small_scene
+    ck, hk, dk = CASES[case]
+    cam, hole = U.Camera(**ck), U.BlackHole(**hk)
+    det = U.RayDetails(integration_method=method, model_count=1, time=1.25, **dk)
+    w, h = 33, 19                                     # odd width: the last pixel of a row is a pair with one ray
+    rgba, hit, steps, st = host_pass(host_kernel_pair, 2, tex, blob, w, h, cam, hole, det)
+    ora = oracle.ray_pass(small_oracle_scene, w, h, cam.uniform(), hole.uniform(), det.uniform(), flavour="fused")
     same = bits(rgba) == bits(ora.rgba)
     assert same.all(), f"{case}: {(~same).mean():.3%} of RGBA words differ"
     assert np.array_equal(hit, ora.hit) and np.array_equal(steps, ora.steps)
