@@ -1,7 +1,8 @@
 """The product's device source on the CPU, against the oracle — no GPU needed.
 
 tests/host_kernel/host_kernel.cpp compiles bhusie_b200/csrc/ray_impl.cuh + detmath.cuh with g++ (one lane per "warp",
-warp votes / atomics / packed-FP32 intrinsics emulated one IEEE operation each) and runs trace_warp pixel by pixel.  What
+warp votes / atomics / packed-FP32 intrinsics emulated one IEEE operation each) and runs trace_warp pixel by pixel;
+tests/host_kernel/host_warp.cpp runs the kernels themselves as one warp of 32 host threads in lock-step.  What
 this pins without a GPU is the LOGIC of the kernel's state machine — the speculative quiet step, the literal tail, the
 event / shading / flat-space phases, the cold rows — and its arithmetic as written, bit for bit against the oracle flavour
 of the numeric mode.  What it cannot see is anything ptxas or the hardware adds (contraction, MUFU seeds, scheduling): that
@@ -115,3 +116,100 @@ def test_two_ray_kernel_source_on_cpu_matches_oracle(host_kernel_pair, oracle, s
     assert np.array_equal(hit, ora.hit) and np.array_equal(steps, ora.steps)
     for k in ("steps", "px_traced", "node_visits", "tri_tests", "tex_samples", "rk_reject", "stack_overflow"):
         assert st[k] == ora.counters[k], (k, st[k], ora.counters[k])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The whole kernels as one warp of 32 host threads in lock-step (tests/host_kernel/host_warp.cpp): persistent work loop,
+# phase sorting, batched disk shading, narrow work items, classification + ballot-compacted trace queue, sky resolve.
+SRC_WARP = os.path.join(ROOT, "tests", "host_kernel", "host_warp.cpp")
+OUT_WARP = os.path.join(ROOT, "tests", "host_kernel", "_build", "libbh_host_warp.so")
+
+
+@pytest.fixture(scope="session")
+def host_warp():
+    cuda_inc = "/usr/local/cuda/include"
+    if not os.path.isdir(cuda_inc):
+        pytest.skip("CUDA headers not found")
+    deps = DEPS + [SRC_WARP]
+    if not os.path.exists(OUT_WARP) or any(os.path.getmtime(d) > os.path.getmtime(OUT_WARP) for d in deps):
+        os.makedirs(os.path.dirname(OUT_WARP), exist_ok=True)
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        cmd = [cxx, "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-fno-fast-math", "-march=x86-64-v3",
+               "-I", cuda_inc, "-x", "c++", SRC_WARP, "-o", OUT_WARP]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr[-4000:]
+    lib = C.CDLL(OUT_WARP)
+    lib.bh_host_warp_level.restype = C.c_int
+    return lib
+
+
+def warp_level(lib, mode, tex, blob, w, h, cam, hole, det, prev=None, tile_rows=4, want_sky=False):
+    rgba = np.zeros((h, w, 4), np.float32)
+    hit = np.full((h, w), -7, np.int32)
+    steps = np.full((h, w), 12345, np.uint32)
+    cls = np.full((h, w), 9, np.uint8)
+    stats = np.zeros(9, np.uint64)
+    sky = np.zeros((h, w, 4), np.float32) if want_sky else None
+    p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    t = {k: np.ascontiguousarray(tex[k]) for k in ("color", "disk", "sky")}
+    prev = None if prev is None else np.ascontiguousarray(prev, dtype=np.float32)
+    ph, pw = (0, 0) if prev is None else prev.shape[:2]
+    rc = lib.bh_host_warp_level(C.c_int(mode), C.c_char_p(cam.uniform()), C.c_char_p(hole.uniform()), C.c_char_p(det.uniform()),
+                                p(t["color"]), C.c_int(t["color"].shape[1]), C.c_int(t["color"].shape[0]),
+                                p(t["disk"]), C.c_int(t["disk"].shape[1]), C.c_int(t["disk"].shape[0]),
+                                p(t["sky"]), C.c_int(t["sky"].shape[1]), C.c_int(t["sky"].shape[0]),
+                                p(blob), C.c_int(w), C.c_int(h), p(prev), C.c_int(pw), C.c_int(ph), C.c_int(tile_rows),
+                                p(rgba), p(hit), p(steps), p(cls), p(stats), p(sky))
+    assert rc == 0
+    return rgba, hit, steps, cls, dict(zip(STAT_NAMES, (int(x) for x in stats))), sky
+
+
+def _assert_level(what, got, ora):
+    rgba, hit, steps, cls, st = got
+    same = bits(rgba) == bits(ora.rgba)
+    assert same.all(), f"{what}: {(~same).mean():.3%} of RGBA words differ"
+    assert np.array_equal(hit, ora.hit), what
+    assert np.array_equal(steps, ora.steps), what
+    assert np.array_equal(cls, ora.cls), what
+    for k in STAT_NAMES[:7] + ("rk_reject", "stack_overflow"):
+        assert st[k] == ora.counters[k], (what, k, st[k], ora.counters[k])
+
+
+@pytest.mark.parametrize("mode", [0, 1], ids=["literal", "fused"])
+@pytest.mark.parametrize("method", [0, 1], ids=["euler", "rk"])
+def test_kernels_as_a_lockstep_warp_pyramid_and_sky(host_warp, oracle, small_scene, small_oracle_scene, mode, method):
+    """Three pyramid levels (S_n = 3 S_{n-1} - 2) + sky resolve through the real trace_kernel / classify_kernel / sky_kernel
+    control flow, each level fed with the previous one's output, against the oracle: pixels, hit indices, step counts,
+    pixel classes and pass statistics bit for bit."""
+    tex, blob, _ = small_scene
+    cam, hole = U.Camera(), U.BlackHole()
+    det = U.RayDetails(integration_method=method, model_count=1, time=0.5, angle_division_threshold=0.08)
+    prev_dev, prev_ora = None, None
+    sizes = U.pyramid_levels(base=(12, 7), iters=3)
+    for li, (w, h) in enumerate(sizes):
+        last = li == len(sizes) - 1
+        rgba, hit, steps, cls, st, sky = warp_level(host_warp, mode, tex, blob, w, h, cam, hole, det, prev=prev_dev, want_sky=last)
+        ora = oracle.ray_pass(small_oracle_scene, w, h, cam.uniform(), hole.uniform(), det.uniform(), prev=prev_ora, flavour=FLAVOUR[mode])
+        if last:                                      # the sky kernel added its texture samples to the same counters
+            o32, _, sc = oracle.sky_pass(small_oracle_scene, ora.rgba, flavour=FLAVOUR[mode])
+            st = dict(st, tex_samples=st["tex_samples"] - sc["tex_samples"])
+            assert np.array_equal(bits(sky), bits(o32)), "sky resolve"
+        _assert_level(f"level {li} {w}x{h}", (rgba, hit, steps, cls, st), ora)
+        if li > 0:
+            assert st["px_copied"] > 0 and st["px_interp"] + st["px_traced"] > 0
+        prev_dev, prev_ora = rgba, ora.rgba
+
+
+@pytest.mark.parametrize("tile_rows", [4, 2, 1])
+@pytest.mark.parametrize("case", ["default", "outside_sphere", "near_hole", "grazing_plane"])
+def test_kernels_as_a_lockstep_warp_single_level(host_warp, oracle, small_scene, small_oracle_scene, tile_rows, case):
+    """Base level in tile mode with 32, 16 and 8 rays per warp (the narrow work items of launches that do not fill the GPU),
+    ragged frame edges included."""
+    tex, blob, _ = small_scene
+    ck, hk, dk = CASES[case]
+    cam, hole = U.Camera(**ck), U.BlackHole(**hk)
+    det = U.RayDetails(integration_method=1, model_count=1, time=1.25, **dk)
+    w, h = 21, 10
+    rgba, hit, steps, cls, st, _ = warp_level(host_warp, 1, tex, blob, w, h, cam, hole, det, tile_rows=tile_rows)
+    ora = oracle.ray_pass(small_oracle_scene, w, h, cam.uniform(), hole.uniform(), det.uniform(), flavour="fused")
+    _assert_level(f"{case} rows {tile_rows}", (rgba, hit, steps, cls, st), ora)
