@@ -133,7 +133,8 @@ extern "C" int bh_host_warp_level(int mode, const void *camera, const void *hole
                                   const uint8_t *sky, int sw, int sh, const unsigned char *models,
                                   int w, int h, const float *prev, int pw, int ph, int tile_rows,
                                   float *out_rgba, int32_t *out_hit, uint32_t *out_steps, uint8_t *out_class,
-                                  unsigned long long *stats9, float *sky_rgba32f)
+                                  unsigned long long *stats9, float *sky_rgba32f,
+                                  int band_rows, int rank, int n_ranks, int local_rows, int out_global_rows)
 {
     using namespace bh;
     PassParams P;
@@ -149,15 +150,19 @@ extern "C" int bh_host_warp_level(int mode, const void *camera, const void *hole
     P.out = reinterpret_cast<float4 *>(out_rgba);
     P.prev = reinterpret_cast<const float4 *>(prev);
     P.w = w; P.h = h; P.pw = prev ? pw : 1; P.ph = prev ? ph : 1;
-    P.band_rows = h; P.rank = 0; P.n_ranks = 1; P.local_rows = h;
+    // image-space sharding (bh_ray_pipeline_set_tiling / bind_frame): n_ranks <= 1 is the whole frame.  With out_global_rows the
+    // pixels go to their global row of a full w x h frame (the peer-store exchange); the aux planes stay band-major.
+    if (n_ranks <= 1) { band_rows = h; rank = 0; n_ranks = 1; local_rows = h; out_global_rows = 0; }
+    P.band_rows = band_rows; P.rank = rank; P.n_ranks = n_ranks; P.local_rows = local_rows;
+    P.out_global_rows = out_global_rows;
     P.aux_hit = out_hit; P.aux_steps = out_steps; P.aux_class = out_class;
     P.tiles_x = (w + 7) / 8;
     P.tile_rows = (unsigned)tile_rows;
     P.item_begin = 0;
-    P.n_items = (unsigned)P.tiles_x * (unsigned)((h + tile_rows - 1) / tile_rows);
+    P.n_items = (unsigned)P.tiles_x * (unsigned)((local_rows + tile_rows - 1) / tile_rows);
     unsigned long long stats[kStatCount] = { 0 };
     unsigned work[kWorkCount] = { 0 };
-    std::vector<unsigned> queue((size_t)w * (size_t)h + 1);
+    std::vector<unsigned> queue((size_t)w * (size_t)local_rows + 1);
     P.stats = stats; P.work = work; P.queue = queue.data();
     {   // same expression as build_pass_params (bh_abi.cu)
         const float *n = P.hole.normal;
@@ -188,7 +193,7 @@ extern "C" int bh_host_warp_level(int mode, const void *camera, const void *hole
     if (sky_rgba32f) {
         SkyParams S;
         memset(&S, 0, sizeof S);
-        S.sky = P.sky; S.prev = P.out; S.out = sky_rgba32f; S.n_pixels = w * h; S.format = BH_SKY_RGBA32F; S.stats = stats;
+        S.sky = P.sky; S.prev = P.out; S.out = sky_rgba32f; S.n_pixels = w * (out_global_rows ? h : local_rows); S.format = BH_SKY_RGBA32F; S.stats = stats;
         run_warp([&] { if (mode == 0) lit::sky_kernel(S); else fus::sky_kernel(S); });
     }
     if (stats9) memcpy(stats9, stats, sizeof stats);

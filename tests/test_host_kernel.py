@@ -143,11 +143,15 @@ def host_warp():
     return lib
 
 
-def warp_level(lib, mode, tex, blob, w, h, cam, hole, det, prev=None, tile_rows=4, want_sky=False):
-    rgba = np.zeros((h, w, 4), np.float32)
-    hit = np.full((h, w), -7, np.int32)
-    steps = np.full((h, w), 12345, np.uint32)
-    cls = np.full((h, w), 9, np.uint8)
+def warp_level(lib, mode, tex, blob, w, h, cam, hole, det, prev=None, tile_rows=4, want_sky=False, tiling=None, frame=None):
+    """tiling = (band_rows, rank, n_ranks): this rank's cyclic bands only, band-major outputs of local_rows rows; with `frame`
+    (a full h x w x 4 array) the pixels go to their global rows of it instead (the peer-store exchange)."""
+    from bhusie_b200.multi import BandLayout
+    rows = h if tiling is None else BandLayout(h, tiling[0], tiling[2]).local_rows(tiling[1])
+    rgba = np.zeros((rows, w, 4), np.float32) if frame is None else frame
+    hit = np.full((rows, w), -7, np.int32)
+    steps = np.full((rows, w), 12345, np.uint32)
+    cls = np.full((rows, w), 9, np.uint8)
     stats = np.zeros(9, np.uint64)
     sky = np.zeros((h, w, 4), np.float32) if want_sky else None
     p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
@@ -159,7 +163,8 @@ def warp_level(lib, mode, tex, blob, w, h, cam, hole, det, prev=None, tile_rows=
                                 p(t["disk"]), C.c_int(t["disk"].shape[1]), C.c_int(t["disk"].shape[0]),
                                 p(t["sky"]), C.c_int(t["sky"].shape[1]), C.c_int(t["sky"].shape[0]),
                                 p(blob), C.c_int(w), C.c_int(h), p(prev), C.c_int(pw), C.c_int(ph), C.c_int(tile_rows),
-                                p(rgba), p(hit), p(steps), p(cls), p(stats), p(sky))
+                                p(rgba), p(hit), p(steps), p(cls), p(stats), p(sky),
+                                *(C.c_int(v) for v in ((0, 0, 0, h, 0) if tiling is None else (tiling[0], tiling[1], tiling[2], rows, int(frame is not None)))))
     assert rc == 0
     return rgba, hit, steps, cls, dict(zip(STAT_NAMES, (int(x) for x in stats))), sky
 
@@ -213,3 +218,31 @@ def test_kernels_as_a_lockstep_warp_single_level(host_warp, oracle, small_scene,
     rgba, hit, steps, cls, st, _ = warp_level(host_warp, 1, tex, blob, w, h, cam, hole, det, tile_rows=tile_rows)
     ora = oracle.ray_pass(small_oracle_scene, w, h, cam.uniform(), hole.uniform(), det.uniform(), flavour="fused")
     _assert_level(f"{case} rows {tile_rows}", (rgba, hit, steps, cls, st), ora)
+
+
+@pytest.mark.parametrize("band,world", [(4, 3), (5, 2)])
+def test_kernels_as_a_lockstep_warp_tiled_ranks(host_warp, oracle, small_scene, small_oracle_scene, band, world):
+    """Image-space sharding inside the kernels: every rank traces only its cyclic row bands — once into its
+    compact band-major buffer (the NCCL-gather exchange), once straight into the global rows of one shared frame (the
+    peer-store exchange) — and the assembled frame is the single-rank frame, bit for bit, on a two-level pyramid."""
+    from bhusie_b200.multi import BandLayout
+    tex, blob, _ = small_scene
+    cam, hole = U.Camera(), U.BlackHole()
+    det = U.RayDetails(integration_method=1, model_count=1, angle_division_threshold=0.08)
+    (w0, h0), (w1, h1) = U.pyramid_levels(base=(11, 8), iters=2)
+    ora0 = oracle.ray_pass(small_oracle_scene, w0, h0, cam.uniform(), hole.uniform(), det.uniform(), flavour="fused")
+    ora1 = oracle.ray_pass(small_oracle_scene, w1, h1, cam.uniform(), hole.uniform(), det.uniform(), prev=ora0.rgba, flavour="fused")
+    for (w, h, prev, ora) in ((w0, h0, None, ora0), (w1, h1, ora0.rgba, ora1)):
+        lay = BandLayout(h, band, world)
+        shared = np.zeros((h, w, 4), np.float32)
+        gathered = np.zeros((h, w, 4), np.float32)
+        steps_total = 0
+        for rank in range(world):
+            rgba, hit, steps, cls, st, _ = warp_level(host_warp, 1, tex, blob, w, h, cam, hole, det, prev=prev, tiling=(band, rank, world))
+            rows = lay.rows_of(rank)
+            gathered[rows] = rgba
+            assert np.array_equal(hit, ora.hit[rows]) and np.array_equal(steps, ora.steps[rows]) and np.array_equal(cls, ora.cls[rows])
+            steps_total += st["steps"]
+            warp_level(host_warp, 1, tex, blob, w, h, cam, hole, det, prev=prev, tiling=(band, rank, world), frame=shared)
+        assert steps_total == ora.counters["steps"]
+        assert np.array_equal(bits(gathered), bits(ora.rgba)) and np.array_equal(bits(shared), bits(ora.rgba))
