@@ -246,3 +246,63 @@ def test_kernels_as_a_lockstep_warp_tiled_ranks(host_warp, oracle, small_scene, 
             warp_level(host_warp, 1, tex, blob, w, h, cam, hole, det, prev=prev, tiling=(band, rank, world), frame=shared)
         assert steps_total == ora.counters["steps"]
         assert np.array_equal(bits(gathered), bits(ora.rgba)) and np.array_equal(bits(shared), bits(ora.rgba))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Post chain: csrc/post_impl.cuh thread by thread over its launch grid (tests/host_kernel/host_post.cpp)
+SRC_POST = os.path.join(ROOT, "tests", "host_kernel", "host_post.cpp")
+OUT_POST = os.path.join(ROOT, "tests", "host_kernel", "_build", "libbh_host_post.so")
+
+
+@pytest.fixture(scope="session")
+def host_post():
+    cuda_inc = "/usr/local/cuda/include"
+    if not os.path.isdir(cuda_inc):
+        pytest.skip("CUDA headers not found")
+    deps = DEPS + [SRC_POST, os.path.join(ROOT, "bhusie_b200", "csrc", "post_impl.cuh")]
+    if not os.path.exists(OUT_POST) or any(os.path.getmtime(d) > os.path.getmtime(OUT_POST) for d in deps):
+        os.makedirs(os.path.dirname(OUT_POST), exist_ok=True)
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        cmd = [cxx, "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-march=x86-64-v3",
+               "-I", cuda_inc, "-x", "c++", SRC_POST, "-o", OUT_POST]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr[-4000:]
+    lib = C.CDLL(OUT_POST)
+    lib.bh_host_post_pass.restype = C.c_int
+    return lib
+
+
+def post_pass(lib, mode, kind, in1, out_w, out_h, in2=None, mix_ratio=0.0, fxaa=None):
+    in1 = np.ascontiguousarray(in1, dtype=np.uint16)
+    in2 = None if in2 is None else np.ascontiguousarray(in2, dtype=np.uint16)
+    out = np.zeros((out_h, out_w, 4), np.uint8 if kind == 4 else np.uint16)
+    p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    rc = lib.bh_host_post_pass(C.c_int(mode), C.c_int(kind), p(in1), C.c_int(in1.shape[1]), C.c_int(in1.shape[0]), p(in2),
+                               p(out), C.c_int(out_w), C.c_int(out_h), C.c_float(mix_ratio), None if fxaa is None else C.c_char_p(fxaa))
+    assert rc == 0
+    return out
+
+
+@pytest.mark.parametrize("mode", [0, 1], ids=["literal", "fused"])
+def test_post_chain_source_on_cpu_matches_oracle(host_post, host_warp, oracle, small_scene, small_oracle_scene, mode):
+    """Every stage of the post chain — 10 bloom levels, mix, ACES, FXAA — computed by the product's kernels on the CPU from
+    the oracle's previous stage, equal to the oracle's stage bit for bit (RGBA16F bits / RGBA8 bytes)."""
+    from bhusie_b200.post import FXAADetails, bloom_sizes
+    tex, blob, _ = small_scene
+    cam, hole = U.Camera(), U.BlackHole()
+    det = U.RayDetails(integration_method=1, model_count=1)
+    w, h = 76, 43
+    ray = oracle.ray_pass(small_oracle_scene, w, h, cam.uniform(), hole.uniform(), det.uniform(), flavour=FLAVOUR[mode])
+    _, sky16, _ = oracle.sky_pass(small_oracle_scene, ray.rgba, flavour=FLAVOUR[mode])
+    sizes = bloom_sizes((w, h))
+    fx = FXAADetails().uniform()
+    ora = oracle.post_chain(sky16, sizes, 0.7, fx, flavour=FLAVOUR[mode])
+    cur = sky16
+    n = len(sizes) // 2
+    for i, (bw, bh_) in enumerate(sizes):
+        got = post_pass(host_post, mode, 0 if i < n else 1, cur, bw, bh_)
+        assert np.array_equal(got, ora["bloom"][i]), f"bloom level {i} ({bw}x{bh_})"
+        cur = ora["bloom"][i]
+    assert np.array_equal(post_pass(host_post, mode, 2, sky16, w, h, in2=cur, mix_ratio=0.7), ora["mix"]), "mix"
+    assert np.array_equal(post_pass(host_post, mode, 3, ora["mix"], w, h), ora["hdr"]), "hdr"
+    assert np.array_equal(post_pass(host_post, mode, 4, ora["hdr"], w, h, fxaa=fx), ora["fxaa"]), "fxaa"
