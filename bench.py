@@ -10,15 +10,24 @@ lucy.obj BVH, every pixel traced (single level), default camera — through RayP
 Prints ONE JSON line (rank 0).  Metric: Mray-steps/s (one ray-step = one next_ray_rk call,
 ray.wgsl:528); fps = 1000 / ms_per_step is reported beside it.
 
-  value      whole-job ray-steps/s with the scene resident in HBM (device-timed, max over ranks)
-  e2e        same metric through the public API with HOST buffers: per step the ModelUniform blob
-             (48 MB — the reference re-sends it every frame, array_buffer.rs:71-79) goes H2D from
-             pinned memory, the pass runs, and the RGBA32F frame lands in pinned host memory (zero-copy stores over PCIe
-             while the kernel traces; --e2e-chunks k for banded cudaMemcpyAsync instead)
-  roofline   HBM bound per BASELINE.md §4: algorithmic bytes (256 B per ray-step + ...) / kernel time
+  value          whole-job ray-steps/s with the scene resident in HBM (device-timed, max over ranks), FUSED numeric mode
+  value_literal  the same measurement in LITERAL numeric mode (one IEEE op per WGSL node), ms_per_step_literal beside it
+  e2e            same metric through the public API with HOST buffers: per step the ModelUniform blob
+                 (48 MB — the reference re-sends it every frame, array_buffer.rs:71-79) goes H2D from
+                 pinned memory, the pass runs, and the RGBA32F frame lands in page-locked host memory: the kernel's pixel
+                 stores go there directly over PCIe while it traces.  N > 1: ONE host frame in POSIX shared memory that
+                 every rank maps, so each rank uses its own PCIe link.  e2e_header_only: the variant that sends the 16-byte
+                 model header instead of the blob (bh_ctx_set_model_header)
+  roofline       the limit the hot kernel actually runs against — warp-instruction issue — from the committed ncu
+                 capture of THIS kernel source (profiles/trace_kernel_dram.json, refused when its source hash is stale);
+                 achieved_dram_gbs = measured DRAM traffic / kernel time; roofline_hbm_streamed = the SURVEY §8d
+                 accounting (256 B per ray-step as if the state were streamed through HBM)
+  parity         (N = 1) 48 rows of the timed 4K frame against the oracle: bit-exact vs the mode's flavour, outlier
+                 fraction / max-abs vs the strict libm flavour, share of outliers the float64 shadow marks ill-conditioned
+  pyramid        (N = 1) the reference's own frame: 4-level adaptive grid 72x41 -> 1918x1081 + sky (+ post chain), Euler and RK
   cpu_baseline / --impl reference: the CPU restatement of the reference pass (oracle, strict libm
-             flavour, OpenMP on all host cores) on a bounded sample of the same workload.  The
-             reference itself (Rust + wgpu/lavapipe) cannot run here.
+                 flavour, OpenMP on all host cores) on a bounded sample of the same workload.  The
+                 reference itself (Rust + wgpu/lavapipe) cannot run here.
 """
 from __future__ import annotations
 
@@ -40,6 +49,16 @@ UNIT = "Mray-steps/s"
 WORKLOAD = "C3: 3840x2160 single-level adaptive-RK (Cash-Karp), disk + relativity sphere + lucy.obj 99970-tri BVH, default camera (0,0,-19)"
 CPU_SAMPLE_RES = (1920, 1080)     # cpu_baseline sample: same scene and camera at 1/4 area
 REF_STEP_RES = (960, 540)         # --impl reference: each step is a 1/16-area frame of the same scene
+STAT_KEYS = ("ray_steps", "node_visits", "tri_tests", "tex_samples", "px_traced")
+
+
+def host_threads() -> int:
+    """Cores this process may use.  torch.distributed.run exports OMP_NUM_THREADS=1 to its workers; the CPU arm must not
+    inherit that."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
 
 
 def peaks():
@@ -100,11 +119,10 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def load_scene(need_mesh: bool = True):
+def load_scene():
+    """Textures + mesh through the PRODUCT's host code (libbhray.so's OBJ loader / BVH builder)."""
     from bhusie_b200 import assets, pipelines as P
     tex, tex_src = assets.load_textures()
-    if not need_mesh:
-        return tex, tex_src, None, "none", {}
     if assets.have_lucy():
         blob, info = P.load_obj_model(assets.lucy_path())
         mesh_src = "lucy.obj"
@@ -114,22 +132,45 @@ def load_scene(need_mesh: bool = True):
     return tex, tex_src, blob, mesh_src, info
 
 
-def cpu_oracle_rate(tex, blob, res, nthreads=0, repeats=1):
+def load_scene_oracle():
+    """The same scene built with the ORACLE's own OBJ loader / BVH builder: the reference arm never maps libbhray.so."""
+    from bhusie_b200 import assets                  # pure Python (PNG decode, synthetic fallbacks): loads no native library
+    from oracle import oracle as O
+    tex, tex_src = assets.load_textures()
+    if assets.have_lucy():
+        blob, _ = O.load_obj(assets.lucy_path())
+        mesh_src = "lucy.obj"
+    else:
+        pts, nrm, tris = assets.uv_sphere()
+        blob = O.new_model_blob()
+        v = O.blob_views(blob)
+        v["points"][: len(pts), :3] = pts
+        v["normals"][: len(nrm), :3] = nrm
+        v["triangles"][: len(tris)] = tris
+        v["position"][:] = (-10.0, 0.0, 30.0)
+        v["visible"][0] = 1
+        hdr = blob[:48].view(np.int32)
+        hdr[8], hdr[10] = len(pts), len(tris)
+        O.build_bvh(blob, len(tris))
+        mesh_src = "synthetic uv_sphere 224x224 (lucy.obj not staged)"
+    return tex, tex_src, blob, mesh_src
+
+
+def cpu_oracle_rate(tex, blob, res, nthreads, repeats=1):
     """Times the oracle (strict flavour) on one frame of `res`; returns (steps/s, steps, seconds, threads)."""
     from bhusie_b200 import uniforms as U
     from oracle import oracle as O
     sc = O.OracleScene(tex["color"], tex["disk"], tex["sky"], blob)
     cam, hole = U.Camera().uniform(), U.BlackHole().uniform()
     det = U.RayDetails(integration_method=1, model_count=1 if blob is not None else 0).uniform()
-    threads = nthreads or O.max_threads()
     best, steps = None, 0
     for _ in range(repeats):
         t0 = time.perf_counter()
-        r = O.ray_pass(sc, res[0], res[1], cam, hole, det, flavour="strict", nthreads=threads)
+        r = O.ray_pass(sc, res[0], res[1], cam, hole, det, flavour="strict", nthreads=nthreads)
         dt = time.perf_counter() - t0
         steps = r.counters["steps"]
         best = dt if best is None else min(best, dt)
-    return steps / best, steps, best, threads
+    return steps / best, steps, best, nthreads
 
 
 def run_reference(args):
@@ -137,10 +178,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    tex, tex_src, blob, mesh_src, _ = load_scene()
+    threads = host_threads()
+    os.environ["OMP_NUM_THREADS"] = str(threads)          # before libgomp initialises (the oracle library is not loaded yet)
+    os.environ.pop("OMP_THREAD_LIMIT", None)
     from oracle import oracle as O
     O.build()
-    threads = O.max_threads()
+    tex, tex_src, blob, mesh_src = load_scene_oracle()
     for _ in range(args.warmup):
         cpu_oracle_rate(tex, blob, REF_STEP_RES, threads)
     t_total, steps_total = 0.0, 0
@@ -155,7 +198,8 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1000.0 * t_total / max(args.steps, 1), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": f"synthetic camera path; textures={tex_src}; mesh={mesh_src}",
         "config": {"workload": WORKLOAD, "reference_arm": "CPU restatement of ray.wgsl (oracle/bh_oracle.c, strict libm flavour, OpenMP); "
-                   "the Rust/wgpu reference cannot be built or run here (no cargo, no Vulkan ICD)", "sample": sample},
+                   "the Rust/wgpu reference cannot be built or run here (no cargo, no Vulkan ICD)", "sample": sample,
+                   "mesh_loader": "oracle's own bho_load_obj / bho_build_bvh (libbhray.so is not loaded by this arm)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "fps_extrapolated_3840x2160": None,
@@ -164,11 +208,97 @@ def run_reference(args):
     return 0
 
 
+def kernel_constants(numeric_mode: str):
+    """Per-warp-step counts of the hot kernel from the committed ncu capture — only when it was taken from THIS source."""
+    from bhusie_b200 import build as B
+    prof = os.path.join(ROOT, "profiles", "trace_kernel_dram.json")
+    try:
+        with open(prof) as f:
+            pj = json.load(f).get(numeric_mode, {})
+    except Exception:
+        return {}, "profiles/trace_kernel_dram.json unreadable"
+    have, want = pj.get("source_hash"), B.kernel_source_hash()
+    if have != want:
+        return {}, f"stale: capture is of kernel source {have}, this build is {want} (re-run tools/capture_constants.sh)"
+    return pj, "current"
+
+
+def parity_block(ctx, P, U, tex, blob, W, H, cam, hole, det, n_rows=48):
+    """48 rows of the headline frame, device vs oracle (the oracle is the checker here, never the thing measured)."""
+    from oracle import oracle as O
+    osc = O.OracleScene(tex["color"], tex["disk"], tex["sky"], blob)
+    rows = sorted(set(np.linspace(0, H - 1, n_rows - 8).astype(int).tolist() + [H // 2 + d for d in (-60, -25, -8, -1, 0, 7, 24, 59)]))
+    camb, holeb, detb = cam.uniform(), hole.uniform(), det.uniform()
+    neutral = {}
+    for fl, pert in (("strict", 0.0), ("shadow", 0.0), ("probe", O.SHADOW_PERTURBATION)):
+        neutral[fl] = np.stack([O.ray_pass(osc, W, H, camb, holeb, detb, rows=(y, y + 1), flavour="strict" if fl == "strict" else "shadow",
+                                           perturb=pert).rgba[y] for y in rows])
+    out = {"rows": len(rows), "pixels": len(rows) * W, "tolerance": 1e-4,
+           "how": "rows of the timed 3840x2160 frame; oracle flavours computed on the host for the same rows; ill-conditioned = the strict f32 "
+                  "evaluation is off its float64 shadow by > tol, or a 1e-6 rad rotation of the camera ray moves the float64 result by > tol; "
+                  "whole-frame figures for every BASELINE config: profiles/r2_parity_report.json"}
+    mode0 = ctx.numeric_mode
+    for mode, name in ((P.NUMERIC_FUSED, "fused"), (P.NUMERIC_LITERAL, "literal")):
+        ctx.set_numeric_mode(mode)
+        rp = P.RayPipeline(ctx, W, H, aux=P.AUX_HIT | P.AUX_STEPS)
+        rp.pass_(cam, hole, det)
+        dev = rp.read()
+        rp.close()
+        fl = P.ORACLE_FLAVOUR_OF_MODE[mode]
+        exact = True
+        for y in rows:
+            o = O.ray_pass(osc, W, H, camb, holeb, detb, rows=(y, y + 1), flavour=fl)
+            exact = exact and bool(np.array_equal(dev["rgba"][y].view(np.uint32), o.rgba[y].view(np.uint32))
+                                   and np.array_equal(dev["hit"][y], o.hit[y]) and np.array_equal(dev["steps"][y], o.steps[y]))
+        rep = O.parity_report(dev["rgba"][rows], neutral["strict"], neutral["shadow"], 1e-4, neutral["probe"])
+        out[name] = {"bit_exact_vs_oracle_flavour": exact, "oracle_flavour": fl, "vs_strict_outlier_frac": rep["outlier_frac"],
+                     "vs_strict_max_abs": rep["max_abs"], "vs_strict_rms": rep["rms"],
+                     "outliers_ill_conditioned_share": rep["outliers_ill_conditioned_share"],
+                     "outlier_frac_well_conditioned": rep["outlier_frac_well_conditioned"]}
+    ctx.set_numeric_mode(mode0)
+    return out
+
+
+def pyramid_block(ctx, P, U, torch, stream, reps=20):
+    """The reference's own frame (mod.rs:170-216, 406-431): 4 levels 72x41 -> 1918x1081, sky resolve, post chain."""
+    from bhusie_b200.post import PostChain
+    cam, hole = U.Camera(), U.BlackHole()
+    out = {"what": "4-level adaptive grid 72x41->1918x1081 (x3-2) + Rgba16Float sky resolve; post = bloom x10 + mix + ACES + FXAA; "
+                   "device-timed, mean of %d frames; 4k = base 143x81 -> 3835x2161" % reps}
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    for name, base in (("reference_1918x1081", (72, 41)), ("4k_3835x2161", (143, 81))):
+        for method, mname in ((0, "euler"), (1, "rk")):
+            det = U.RayDetails(integration_method=method, model_count=1)
+            pyr = P.RayPyramid(ctx, base=base)
+            chain = PostChain(ctx, pyr.sky)
+            ms_ray = timed(lambda: pyr.pass_(cam, hole, det, stream))
+            ms_all = timed(lambda: (pyr.pass_(cam, hole, det, stream), chain.pass_(stream)))
+            steps = sum(rp.stats()["ray_steps"] for rp in pyr.levels)
+            last = pyr.levels[-1].stats()
+            out[f"{name}_{mname}"] = {"ms_ray_levels_plus_sky": ms_ray, "ms_frame_with_post_chain": ms_all, "fps": 1000.0 / ms_all,
+                                      "ray_steps": steps, "gsteps_per_s": steps / ms_ray / 1e6,
+                                      "last_level_px_traced": last["px_traced"], "last_level_px_interp": last["px_interp"]}
+            chain.close(); pyr.close()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from bhusie_b200 import pipelines as P, uniforms as U
-    from bhusie_b200.multi import TiledFrame
+    from bhusie_b200 import build as B, pipelines as P, uniforms as U
+    from bhusie_b200.multi import HostTiledFrame, TiledFrame
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -202,11 +332,56 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_device():
+    def step_device(fr=frame):
         flush.zero_()                       # L2 flush (256 MiB > 126 MB L2), inside the timed region
-        frame.render(cam, hole, det, stream)        # local bands + (N>1) NCCL gather to rank 0
+        fr.render(cam, hole, det, stream)   # local bands; N > 1: peer stores into rank 0's frame + flag wait (or NCCL gather)
+        fr.consumed(stream)
 
-    # ---------------- device-resident timing
+    def timed_steps(fr, steps, warmup):
+        """(elapsed ms over `steps`, mean kernel ms of this rank) — device events on the launching stream."""
+        for _ in range(warmup):
+            step_device(fr)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0, k1 = [], []
+        e0.record(stream)
+        for _ in range(steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if fr.exchange == "p2p" and fr.rank != 0:
+                fr.render_local(cam, hole, det, stream)     # (begins with the wait for rank 0's "consumed" flag: not kernel time)
+                a = b = None
+            else:
+                a.record(stream)
+                fr.render_local(cam, hole, det, stream)
+                b.record(stream)
+            fr.gather(stream)
+            fr.resolve_sky(stream)
+            fr.consumed(stream)
+            if a is not None:
+                k0.append(a); k1.append(b)
+        e1.record(stream)
+        barrier()
+        ctx.check_async()
+        kernel = float(np.mean([a.elapsed_time(b) for a, b in zip(k0, k1)])) if k0 else 0.0
+        return e0.elapsed_time(e1), kernel
+
+    # ---------------- N > 1: the assembled frame must be bit-identical to a single-GPU render (in the warm-up, not timed)
+    exchange_bit_identical = None
+    if world > 1:
+        step_device()
+        barrier()
+        if rank == 0:
+            single = P.RayPipeline(ctx, W, H)
+            single.pass_(cam, hole, det, stream)
+            ref = torch.as_tensor(_DevPtr(single.output_ptr, (H, W, 4)), device="cuda")
+            torch.cuda.synchronize()
+            exchange_bit_identical = bool(torch.equal(frame.frame_tensor().view(torch.int32), ref.view(torch.int32)))
+            del ref
+            single.close()
+        barrier()
+
+    # ---------------- device-resident timing (FUSED unless --numeric-mode literal)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()                 # sampled from the warm-up on: at N=8 the timed region itself is < 100 ms
@@ -214,21 +389,7 @@ def run_ours(args):
         step_device()
     barrier()
     n_warm_samples = len(sampler.rows)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0, k1 = [], []
-    e0.record(stream)
-    for _ in range(args.steps):
-        flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream)
-        frame.render_local(cam, hole, det, stream)
-        b.record(stream)
-        frame.gather(stream)
-        k0.append(a); k1.append(b)
-    e1.record(stream)
-    barrier()
-    elapsed_ms = e0.elapsed_time(e1)
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(k0, k1)]))
+    elapsed_ms, kernel_ms = timed_steps(frame, args.steps, 0)
     if rank == 0:
         if len(sampler.rows) - n_warm_samples >= 3:
             sampler.rows = sampler.rows[n_warm_samples:]      # enough samples inside the timed region proper
@@ -241,115 +402,190 @@ def run_ours(args):
         clocks = None
     stats = frame.pipeline.stats()
     t = torch.tensor([elapsed_ms, kernel_ms], dtype=torch.float64, device="cuda")
-    s = torch.tensor([stats[k] for k in ("ray_steps", "node_visits", "tri_tests", "tex_samples", "px_traced")], dtype=torch.float64, device="cuda")
+    s = torch.tensor([stats[k] for k in STAT_KEYS], dtype=torch.float64, device="cuda")
     s_local = s.clone()
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
-    elapsed_ms, kernel_ms_max = float(t[0]), float(t[1])
-    total = dict(zip(("ray_steps", "node_visits", "tri_tests", "tex_samples", "px_traced"), (int(x) for x in s.tolist())))
+    elapsed_ms = float(t[0])
+    total = dict(zip(STAT_KEYS, (int(x) for x in s.tolist())))
     ms_per_step = elapsed_ms / args.steps
     value = total["ray_steps"] / (ms_per_step * 1e-3) / 1e6
 
-    # ---------------- end-to-end timing: host buffers, H2D model blob + pass + gather + D2H frame
-    pinned_model = torch.from_numpy(blob).pin_memory()
-    host_frame = torch.empty((H, W, 4), dtype=torch.float32).pin_memory() if rank == 0 else None
+    # ---------------- the other numeric mode, same loop (LITERAL: one IEEE op per WGSL node; the mode whose outliers vs libm are 10x rarer)
+    other = P.NUMERIC_LITERAL if mode == P.NUMERIC_FUSED else P.NUMERIC_FUSED
+    ctx.set_numeric_mode(other)
+    lit_steps = max(3, args.steps // 2)
+    lit_ms, _ = timed_steps(frame, lit_steps, 3)
+    lt = torch.tensor([lit_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(lt, op=dist.ReduceOp.MAX)
+    ms_other = float(lt[0]) / lit_steps
+    ctx.set_numeric_mode(mode)
+    other_name = "literal" if other == P.NUMERIC_LITERAL else "fused"
 
-    def step_e2e():
+    # ---------------- end-to-end timing: host buffers, H2D model blob + pass with the pixels stored straight into the host frame
+    pinned_model = torch.from_numpy(blob).pin_memory()
+    if world == 1:
+        host_frame = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
+        hframe = None
+    else:
+        hframe = HostTiledFrame(ctx, W, H, rank, world, band_rows=args.band_rows)
+        host_frame = None
+
+    def step_e2e(header_only=False):
         flush.zero_()
-        ctx.upload_models_async(pinned_model.data_ptr(), pinned_model.numel(), stream)
+        if header_only:
+            ctx.set_model_header(0, (-10.0, 0.0, 30.0), 1)        # what the UI can change per frame (ui/model_settings.rs:39-48): 16 bytes
+        else:
+            ctx.upload_models_async(pinned_model.data_ptr(), pinned_model.numel(), stream)
         if world == 1:
-            # public API: pass + read-back, the D2H of each row band overlapping the tracing of the next
             frame.pipeline.pass_to_host(cam, hole, det, host_frame.data_ptr(), args.e2e_chunks, stream)
             frame.pipeline.sync()
         else:
-            frame.render(cam, hole, det, stream)
-            if rank == 0:
-                host_frame.copy_(frame.frame_tensor(), non_blocking=True)
-            frame.consumed(stream)
-            stream.synchronize()
+            hframe.render(cam, hole, det, stream)        # every rank: own bands -> the shared host frame over its own PCIe link
+            hframe.consumed()
 
-    for _ in range(max(1, min(args.warmup, 2))):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te[0])
+    def timed_e2e(header_only):
+        for _ in range(max(1, min(args.warmup, 2))):
+            step_e2e(header_only)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e(header_only)
+        barrier()
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return float(te[0])
+
+    e2e_s = timed_e2e(False)
+    e2e_hdr_s = timed_e2e(True)
     e2e_value = total["ray_steps"] * args.steps / e2e_s / 1e6
-    checksum = float(host_frame[::97, ::89].double().sum()) if rank == 0 else 0.0
+    if world > 1:
+        step_device()                       # the device frame in the headline numeric mode again, to compare the host frame with
+        barrier()
+    if rank == 0:
+        hf = host_frame.numpy() if world == 1 else hframe.frame_array()
+        checksum = float(hf[::97, ::89].astype(np.float64).sum())
+        e2e_matches_device = None
+        if world > 1:
+            dev_frame = frame.frame_tensor().cpu().numpy()
+            e2e_matches_device = bool(np.array_equal(dev_frame.view(np.uint32), np.ascontiguousarray(hf).view(np.uint32)))
+            del dev_frame
+    barrier()
+
+    # ---------------- C4 (BASELINE configs[3]): 7680x4320 over the same ranks
+    c4 = None
+    if world > 1 and (args.c4 == "on" or (args.c4 == "auto" and world == 8)):
+        f8 = TiledFrame(ctx, 7680, 4320, rank, world, band_rows=args.band_rows, exchange=args.exchange)
+        c4_steps = max(3, min(args.steps, 8))
+        c4_ms, _ = timed_steps(f8, c4_steps, 3)
+        st8 = f8.pipeline.stats()
+        v8 = torch.tensor([c4_ms, float(st8["ray_steps"])], dtype=torch.float64, device="cuda")
+        vmax = v8.clone()
+        if world > 1:
+            dist.all_reduce(vmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(v8, op=dist.ReduceOp.SUM)
+        c4 = {"workload": "C4: 7680x4320 single-level adaptive-RK, full scene, cyclic row bands over %d GPUs" % world,
+              "ms_per_step": float(vmax[0]) / c4_steps, "fps": 1000.0 * c4_steps / float(vmax[0]), "ray_steps_per_frame": int(v8[1]),
+              "value": float(v8[1]) / (float(vmax[0]) / c4_steps * 1e-3) / 1e6, "unit": UNIT, "steps": c4_steps}
+        f8.close()
+        barrier()
+
+    # ---------------- bh_frame_multi (one process, one host thread, all N devices) checked by rank 0 while the others idle
+    frame_multi = None
+    if world > 1 and rank == 0 and not args.no_frame_multi:
+        try:
+            frame_multi = frame_multi_block(P, U, torch, ctx, tex, blob, world, W, H, args.band_rows, cam, hole, det)
+        except Exception as ex:               # a diagnostic, not the measurement: never lose the line over it
+            frame_multi = {"error": str(ex)[:300]}
+    barrier()
 
     if rank == 0:
         peak, peak_src, peak_json = peaks()
         # roofline for the dominant kernel (trace_kernel) on THIS rank's launch
-        local = dict(zip(("ray_steps", "node_visits", "tri_tests", "tex_samples", "px_traced"), (int(x) for x in s_local.tolist())))
+        local = dict(zip(STAT_KEYS, (int(x) for x in s_local.tolist())))
         n_px_local = frame.pipeline.local_rows * W
         abytes = algorithmic_bytes(local, n_px_local)
-        achieved = abytes / (kernel_ms * 1e-3) / 1e9
-        traffic = None
-        pj = {}
-        # dram__bytes_read.sum + dram__bytes_write.sum, warp instructions, FMA-pipe units and register operand reads per
-        # warp-step: one `ncu --set full` capture of this kernel on this workload (profiles/trace_kernel_dram.json)
-        prof = os.path.join(ROOT, "profiles", "trace_kernel_dram.json")
-        if os.path.exists(prof) and (W, H) == (3840, 2160) and world == 1:
-            try:
-                with open(prof) as f:
-                    pj = json.load(f).get(args.numeric_mode, {})
-                traffic = pj.get("dram_bytes_per_launch")
-            except Exception:
-                traffic, pj = None, {}
+        hbm_achieved = abytes / (kernel_ms * 1e-3) / 1e9
+        pj, pj_state = kernel_constants(args.numeric_mode) if (W, H) == (3840, 2160) else ({}, "constants are for 3840x2160")
+        traffic = pj.get("dram_bytes_per_launch") if world == 1 else None
         inst_per_step = pj.get("warp_inst_per_warp_step")
         fp32_peak_tflops = 148 * 128 * 2 * (peak_json.get("sm_max_mhz", 1965.0) * 1e6) / 1e12
         flops = 400.0 * local["ray_steps"]
+        sm_clock_hz = ((clocks or {}).get("sm_mhz") or peak_json.get("sm_max_mhz", 1965.0)) * 1e6
+        slots = 148 * 4 * sm_clock_hz
+        warp_steps_per_s = (local["ray_steps"] / 32.0) / (kernel_ms * 1e-3)
+        hbm_block = {"bound": "hbm", "achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "frac": hbm_achieved / peak, "traffic": traffic,
+                     "achieved_dram_gbs": (traffic / (kernel_ms * 1e-3) / 1e9) if traffic else None,
+                     "peak_source": peak_src, "kernel": "trace_kernel<1,false,4,origin>", "kernel_ms": kernel_ms,
+                     "algorithmic_bytes_per_launch": abytes,
+                     "note": "SURVEY §8d accounting: 256 B per ray-step as if the 128-byte ray state were streamed through HBM.  The state is "
+                             "register-resident, so these are NOT DRAM bytes (achieved_dram_gbs is the measured DRAM rate) and frac > 1 "
+                             "only says the kernel beats any streamed formulation (25.5 G ray-steps/s ceiling)"}
+        if inst_per_step:
+            # DRAM traffic is ~1e-3 of the algorithmic bytes: the binding limit is warp-instruction issue (1 per SM sub-partition
+            # per clock), with the FP32 FMA pipe and register-operand bandwidth within a few % of it
+            roofline = {"bound": "issue", "achieved": inst_per_step * warp_steps_per_s / 1e9, "peak": slots / 1e9, "unit": "G warp-inst/s",
+                        "frac": inst_per_step * warp_steps_per_s / slots, "traffic": traffic,
+                        "achieved_dram_gbs": (traffic / (kernel_ms * 1e-3) / 1e9) if traffic else None, "hbm_peak_gbs": peak,
+                        "warp_inst_per_warp_ray_step": inst_per_step, "kernel": "trace_kernel<1,false,4,origin>", "kernel_ms": kernel_ms,
+                        "constants": f"profiles/trace_kernel_dram.json ({pj_state}; kernel source {pj.get('source_hash')}): ncu --set full capture of this kernel; "
+                                     "time and SM clock measured live",
+                        "peak_source": "148 SM x 4 schedulers x SM clock sampled during the run",
+                        "why_not_hbm": "measured DRAM traffic per launch is the output frame (+ ~10 % scene reads): < 0.2 % of HBM bandwidth"}
+        else:
+            roofline = dict(hbm_block)
+            roofline["constants"] = pj_state
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "fps": 1000.0 / ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": f"synthetic (default camera/black hole uniforms); textures={tex_src}; mesh={mesh_src}",
+            "numeric_mode": args.numeric_mode,
+            f"value_{other_name}": total["ray_steps"] / (ms_other * 1e-3) / 1e6, f"ms_per_step_{other_name}": ms_other,
             "config": {"workload": WORKLOAD if (W, H) == (3840, 2160) else f"{W}x{H} variant of: {WORKLOAD}", "width": W, "height": H,
                        "integrator": "cash-karp-rk", "step_size": 0.15, "max_iterations": 2000, "triangles": mesh_info.get("triangle_count"),
                        "bvh_nodes": mesh_info.get("nodes_used"), "tiling": f"cyclic bands of {frame.band_rows} rows over {world} rank(s)",
-                       "exchange": {"p2p": "ray kernel stores finished pixels directly into rank 0's frame over NVLink (CUDA IPC peer memory) + one 4-byte all-reduce",
+                       "exchange": {"p2p": "ray kernel stores finished pixels directly into rank 0's frame over NVLink (CUDA IPC peer memory); ordering by "
+                                           "stream-ordered flag stores / waits in that memory (no collective in the frame loop)",
                                     "nccl": "NCCL gather of compact band buffers to rank 0 + de-interleave copy", "none": "single GPU"}[frame.exchange],
                        "l2_flush": "256 MiB memset before every step, inside the timed region",
                        "ray_steps_per_frame": total["ray_steps"],
                        "numerics": ("FUSED: explicit fma contraction + reciprocal-multiply, det-math transcendentals (bit-exact vs oracle 'fused')"
                                     if mode == P.NUMERIC_FUSED else
-                                    "LITERAL: one IEEE f32 op per WGSL node, det-math transcendentals (bit-exact vs oracle 'contract')")},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pinned_model.numel() + 196),
+                                    "LITERAL: one IEEE f32 op per WGSL node, det-math transcendentals (bit-exact vs oracle 'contract')"),
+                       "kernel_source_hash": B.kernel_source_hash()},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pinned_model.numel() + 196) * world,
                     "d2h_bytes_per_step": int(W * H * 16), "ms_per_step": 1000.0 * e2e_s / args.steps, "fps": args.steps / e2e_s,
                     "frame_checksum": checksum,
                     "path": ("bh_ctx_upload_models_async + bh_ray_pipeline_pass_to_host("
                              + ("zero-copy: pixel stores land in the pinned host frame over PCIe during the pass" if args.e2e_chunks == 0
                                 else f"{args.e2e_chunks} bands, D2H overlapped") + ") + sync"
-                             if world == 1 else f"upload_models_async + tiled pass ({frame.exchange} exchange) + D2H of the assembled frame")},
-            "gpu_launches": int(args.steps * 1),
+                             if world == 1 else
+                             "per rank: bh_ctx_upload_models_async (48 MB over its own PCIe link) + bh_ray_pipeline_pass_to_host_frame (its bands stored "
+                             "straight into ONE page-locked host frame in POSIX shared memory, bh_host_frame) + host-side flags")},
+            "e2e_header_only": {"value": total["ray_steps"] * args.steps / e2e_hdr_s / 1e6, "unit": UNIT, "ms_per_step": 1000.0 * e2e_hdr_s / args.steps,
+                                "h2d_bytes_per_step": 16 * world + 196 * world, "d2h_bytes_per_step": int(W * H * 16),
+                                "path": "bh_ctx_set_model_header (position + visible, the fields the UI edits) instead of re-sending the 48 MB ModelUniform"},
+            "gpu_launches": int(args.steps * (1 if world == 1 else 2)),
+            "gpu_launches_note": "rank 0, timed region: trace_kernel per step" + ("" if world == 1 else " + the flag-wait kernel (other ranks: wait + trace + signal)"),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "kernel": "trace_kernel<1,false,4,origin>", "kernel_ms": kernel_ms,
-                         "algorithmic_bytes_per_launch": abytes,
-                         "note": "ray state is register-resident: algorithmic bytes (256 B/ray-step, SURVEY §8d) are not DRAM traffic; "
-                                 "frac > 1 means the kernel beats the streamed-state HBM formulation; roofline_issue / roofline_fma_pipe / roofline_regfile are the limits it runs against"},
+            "roofline": roofline,
+            "roofline_hbm_streamed": hbm_block,
             "roofline_fp32": {"bound": "fp32-alu", "achieved": flops / (kernel_ms * 1e-3) / 1e12, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
                               "frac": flops / (kernel_ms * 1e-3) / 1e12 / fp32_peak_tflops, "flops_per_ray_step": 400,
                               "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz (non-tensor FP32, BASELINE.md §2)"},
         }
+        if world > 1:
+            line["exchange_bit_identical"] = exchange_bit_identical
+            line["e2e"]["host_frame_equals_device_frame"] = e2e_matches_device
+        if c4 is not None:
+            line["c4_8k"] = c4
+        if frame_multi is not None:
+            line["frame_multi"] = frame_multi
         if inst_per_step:
-            # The three limits the hot loop actually runs against, all per SM sub-partition and clock: one warp instruction
-            # issued, one FMA-pipe unit (a packed FFMA2/FMUL2/FADD2 is two), two 32-bit register operands per lane read
-            # (tools/ubench/fma_pipe.cu measures the last two).  Per-warp-step counts come from the committed ncu capture of
-            # this kernel (profiles/trace_kernel_dram.json); time and clock are measured live.
-            sm_clock_hz = ((clocks or {}).get("sm_mhz") or peak_json.get("sm_max_mhz", 1965.0)) * 1e6
-            slots = 148 * 4 * sm_clock_hz
-            warp_steps_per_s = (local["ray_steps"] / 32.0) / (kernel_ms * 1e-3)
-            line["roofline_issue"] = {"bound": "warp-instruction issue", "achieved": inst_per_step * warp_steps_per_s / 1e9, "peak": slots / 1e9,
-                                      "unit": "G warp-inst/s", "frac": inst_per_step * warp_steps_per_s / slots,
-                                      "warp_inst_per_warp_ray_step": inst_per_step,
-                                      "peak_source": "148 SM x 4 schedulers x SM clock sampled during the run"}
             if pj.get("fma_pipe_units_per_warp_step"):
                 u = pj["fma_pipe_units_per_warp_step"]
                 line["roofline_fma_pipe"] = {"bound": "FP32 FMA pipe", "achieved": u * warp_steps_per_s / 1e9, "peak": slots / 1e9,
@@ -360,10 +596,19 @@ def run_ours(args):
                 line["roofline_regfile"] = {"bound": "register-file operand bandwidth", "achieved": r * warp_steps_per_s / 1e9, "peak": 2 * slots / 1e9,
                                             "unit": "G operand reads/s", "frac": r * warp_steps_per_s / (2 * slots), "reads_per_warp_ray_step": r,
                                             "peak_source": "2 x 32-bit register source operands per lane per clock per sub-partition (measured)"}
+        if world == 1 and not args.no_extras:
+            try:
+                line["parity"] = parity_block(ctx, P, U, tex, blob, W, H, cam, hole, det)
+            except Exception as ex:
+                line["parity"] = {"error": str(ex)[:300]}
+            try:
+                line["pyramid"] = pyramid_block(ctx, P, U, torch, stream)
+            except Exception as ex:
+                line["pyramid"] = {"error": str(ex)[:300]}
         # CPU baseline beside it (N=1 only): bounded sample of the same workload
         if world == 1 and not args.no_cpu_baseline:
             try:
-                rate, steps_c, dt, threads = cpu_oracle_rate(tex, blob, CPU_SAMPLE_RES)
+                rate, steps_c, dt, threads = cpu_oracle_rate(tex, blob, CPU_SAMPLE_RES, host_threads())
                 line["cpu_baseline"] = {"value": rate / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
                                         "sample": f"{CPU_SAMPLE_RES[0]}x{CPU_SAMPLE_RES[1]} frame of the same scene/camera "
                                                   f"({steps_c} ray-steps, {dt:.1f} s); oracle strict flavour (glibc libm), OpenMP",
@@ -371,10 +616,73 @@ def run_ours(args):
             except Exception as ex:   # the oracle is a checker; its absence must not hide the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"unavailable: {ex}"}
         print(json.dumps(line))
+    if hframe is not None:
+        hframe.close()
     frame.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+class _DevPtr:
+    """__cuda_array_interface__ carrier: lets torch view device memory the library owns."""
+
+    def __init__(self, ptr: int, shape: tuple):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (ptr, False), "version": 2, "strides": None}
+
+
+def frame_multi_block(P, U, torch, ctx0, tex, blob, world, W, H, band_rows, cam, hole, det, reps=5):
+    """bh_frame_multi on all `world` devices from this one process and thread: single-level 4K frame and the reference's
+    4-level adaptive grid, both compared bit for bit with single-GPU renders, plus the frame time."""
+    ctxs = [ctx0]
+    for d in range(1, world):
+        c = P.Context(d, numeric_mode=ctx0.numeric_mode)
+        c.set_textures(tex)
+        c.upload_models(blob)
+        ctxs.append(c)
+    out = {"devices": world, "driver": "one process, one host thread; peer stores into device 0's frame, CUDA events; no torch / NCCL on the path"}
+    try:
+        fm = P.FrameMulti(ctxs, base=(W, H), iters=1, band_rows=band_rows, sky_format=None)
+        fm.pass_(cam, hole, det)
+        got = fm.read(sky=False)["rgba"]
+        single = P.RayPipeline(ctx0, W, H)
+        single.pass_(cam, hole, det)
+        ref = single.read(aux=False)["rgba"]
+        single.close()
+        out["single_level_bit_identical"] = bool(np.array_equal(got.view(np.uint32), ref.view(np.uint32)))
+        for _ in range(3):
+            fm.pass_(cam, hole, det)
+        fm.sync()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fm.pass_(cam, hole, det)
+        fm.sync()
+        out["single_level_ms_per_frame_host_clock"] = 1000.0 * (time.perf_counter() - t0) / reps
+        out["single_level_ms_last_frame_device"] = fm.stats()["elapsed_ms"]
+        fm.close()
+        # the reference's own frame: coarse levels replicated, last level tiled, sky on device 0
+        dete = U.RayDetails(integration_method=0, model_count=1)
+        fp = P.FrameMulti(ctxs, base=(72, 41), iters=4, band_rows=band_rows, sky_format=P.SKY_RGBA16F)
+        fp.pass_(cam, hole, dete)
+        got = fp.read(rgba=False)["sky"]
+        pyr = P.RayPyramid(ctx0)
+        pyr.pass_(cam, hole, dete)
+        ref = pyr.sky.read()
+        pyr.close()
+        out["pyramid_sky_bit_identical"] = bool(np.array_equal(got.view(np.uint16), ref.view(np.uint16)))
+        for _ in range(3):
+            fp.pass_(cam, hole, dete)
+        fp.sync()
+        t0 = time.perf_counter()
+        for _ in range(reps * 2):
+            fp.pass_(cam, hole, dete)
+        fp.sync()
+        out["pyramid_1918x1081_euler_ms_per_frame_host_clock"] = 1000.0 * (time.perf_counter() - t0) / (reps * 2)
+        fp.close()
+    finally:
+        for c in ctxs[1:]:
+            c.close()
+    return out
 
 
 def main():
@@ -392,7 +700,10 @@ def main():
                          "k>0 = k row bands with overlapped cudaMemcpyAsync")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: p2p = kernels store straight into rank 0's frame over NVLink (CUDA IPC); nccl = gather of band buffers")
+    ap.add_argument("--c4", default="auto", choices=["auto", "on", "off"], help="N>1: also time BASELINE configs[3] (7680x4320); auto = at N=8")
+    ap.add_argument("--no-frame-multi", action="store_true", help="N>1: skip rank 0's bh_frame_multi check")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="N=1: skip the parity and pyramid blocks (profiling runs)")
     ap.add_argument("--allow-short-warmup", action="store_true", help="profiling runs only (ncu); numbers from such runs are not bench values")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours" and not args.allow_short_warmup:

@@ -7,6 +7,7 @@ import os
 from . import build as _build
 
 _LIB = None
+ABI_VERSION = 2
 
 
 class BhError(RuntimeError):
@@ -31,8 +32,15 @@ class ModelInfo(C.Structure):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
-# every symbol include/bh_abi.h declares: name -> (restype, argtypes)
 _VP, _U32, _I32 = C.c_void_p, C.c_uint32, C.c_int32
+
+
+class FrameMultiDesc(C.Structure):
+    _fields_ = [("base_width", C.c_uint32), ("base_height", C.c_uint32), ("levels", C.c_uint32), ("multiplier", C.c_uint32),
+                ("band_rows", C.c_uint32), ("sky_format", C.c_int32)]
+
+
+# every symbol include/bh_abi.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "bh_abi_version": (C.c_int, []),
     "bh_last_error": (C.c_char_p, []),
@@ -74,6 +82,29 @@ SYMBOLS = {
     "bh_post_pass_run": (C.c_int, [_VP, _VP, _VP]),
     "bh_post_pass_output": (_VP, [_VP]),
     "bh_post_pass_read": (C.c_int, [_VP, _VP]),
+    "bh_sky_pipeline_create_for_frame": (C.c_int, [_VP, _VP, _U32, _U32, C.c_int, C.POINTER(_VP)]),
+    "bh_frame_multi_create": (C.c_int, [C.POINTER(_VP), _U32, C.POINTER(FrameMultiDesc), C.POINTER(_VP)]),
+    "bh_frame_multi_destroy": (None, [_VP]),
+    "bh_frame_multi_width": (_U32, [_VP]),
+    "bh_frame_multi_height": (_U32, [_VP]),
+    "bh_frame_multi_pass": (C.c_int, [_VP, _VP, _VP, _VP]),
+    "bh_frame_multi_pass_to_host": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
+    "bh_frame_multi_sync": (C.c_int, [_VP]),
+    "bh_frame_multi_output": (_VP, [_VP]),
+    "bh_frame_multi_sky_output": (_VP, [_VP]),
+    "bh_frame_multi_read": (C.c_int, [_VP, _VP, _VP]),
+    "bh_frame_multi_stats": (C.c_int, [_VP, C.POINTER(PassStats), C.POINTER(C.c_float)]),
+    "bh_shared_frame_flags": (_VP, [_VP, C.c_size_t]),
+    "bh_stream_signal": (C.c_int, [_VP, _VP, _U32, _VP]),
+    "bh_stream_wait": (C.c_int, [_VP, _VP, _U32, _U32, _U32, _VP]),
+    "bh_ctx_check_async": (C.c_int, [_VP]),
+    "bh_host_frame_create": (C.c_int, [_VP, C.c_char_p, C.c_size_t, C.c_int, C.POINTER(_VP)]),
+    "bh_host_frame_destroy": (None, [_VP, C.c_int]),
+    "bh_host_frame_ptr": (_VP, [_VP]),
+    "bh_host_frame_signal": (C.c_int, [_VP, _U32, _U32]),
+    "bh_host_frame_wait": (C.c_int, [_VP, _U32, _U32, _U32, _U32]),
+    "bh_ray_pipeline_pass_to_host_frame": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
+    "bh_model_validate": (C.c_int, [_VP]),
     "bh_model_load_obj": (C.c_int, [C.c_char_p, _VP, C.POINTER(ModelInfo)]),
     "bh_model_from_arrays": (C.c_int, [_VP, _I32, _VP, _I32, _VP, _I32, C.POINTER(C.c_float), _I32, _VP, C.POINTER(ModelInfo)]),
     "bh_model_build_bvh": (C.c_int, [_VP, _I32, C.POINTER(ModelInfo)]),
@@ -100,7 +131,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)          # AttributeError here == ABI/header mismatch
             fn.restype = res
             fn.argtypes = args
-        if lib.bh_abi_version() != 1:
+        if lib.bh_abi_version() != ABI_VERSION:
             raise RuntimeError("libbhray.so ABI version mismatch")
         _LIB = lib
     return _LIB

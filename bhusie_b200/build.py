@@ -16,8 +16,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libbhray.so")
-SOURCES = ["bh_abi.cu", "ray_kernels.cu", "model_host.cpp"]
-HEADERS = ["bh_device.h", "detmath.cuh", "ray_impl.cuh", "post_impl.cuh", os.path.join("..", "..", "include", "bh_abi.h")]
+SOURCES = ["bh_abi.cu", "bh_multi.cu", "ray_kernels.cu", "model_host.cpp"]
+HEADERS = ["bh_device.h", "bh_objects.h", "detmath.cuh", "ray_impl.cuh", "ray_pair.cuh", "post_impl.cuh", os.path.join("..", "..", "include", "bh_abi.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -43,6 +43,21 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+KERNEL_SOURCES = ["ray_impl.cuh", "ray_kernels.cu", "detmath.cuh", "bh_device.h", "ray_pair.cuh"]
+
+
+def kernel_source_hash() -> str:
+    """Identifies the device code of the ray pass (sources + the flags that shape it): profiles/trace_kernel_dram.json
+    carries the hash of the source its ncu capture was taken from, and bench.py refuses the constants when it differs."""
+    import hashlib
+    h = hashlib.sha256()
+    for name in KERNEL_SOURCES:
+        with open(os.path.join(CSRC, name), "rb") as f:
+            h.update(name.encode() + b"\0" + f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()[:16]
+
+
 def build_library(force: bool = False, verbose: bool = False, extra: list[str] | None = None, out: str | None = None) -> str:
     """Builds libbhray.so.  `extra`/`out` build an experimental variant (tuning runs) beside the product library."""
     out = out or LIB_PATH
@@ -63,7 +78,9 @@ def build_library(force: bool = False, verbose: bool = False, extra: list[str] |
 
 
 if __name__ == "__main__":
-    if "--pair" in sys.argv:
+    if "--hash" in sys.argv:
+        print(kernel_source_hash())
+    elif "--pair" in sys.argv:
         # the experimental two-rays-per-thread kernel (csrc/ray_pair.cuh) as a second library; run anything against it
         # with BHRAY_LIB=bhusie_b200/lib/libbhray_pair.so (e.g. the whole `pytest -m gpu` suite: it is bit-identical)
         print(build_library(force=True, verbose="--verbose" in sys.argv, extra=["-DBH_USE_PAIR=1"],

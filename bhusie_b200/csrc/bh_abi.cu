@@ -10,7 +10,7 @@
 #include <cstring>
 #include <new>
 
-#include "bh_device.h"
+#include "bh_objects.h"
 
 namespace bh {
 
@@ -24,19 +24,13 @@ void set_error(const char *fmt, ...)
     va_end(ap);
 }
 
-static int cuda_fail(cudaError_t e, const char *what)
+int cuda_fail(cudaError_t e, const char *what)
 {
     set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
     return (e == cudaErrorMemoryAllocation) ? BH_ERR_NOMEM
          : (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice) ? BH_ERR_NODEV
          : BH_ERR_CUDA;
 }
-
-#define BH_CUDA(call)                                             \
-    do {                                                          \
-        cudaError_t e_ = (call);                                  \
-        if (e_ != cudaSuccess) return cuda_fail(e_, #call);       \
-    } while (0)
 
 }  // namespace bh
 
@@ -45,54 +39,6 @@ using namespace bh;
 static_assert(sizeof(bh_camera_uniform) == 32, "CameraUniform is 32 bytes (camera.rs:66-73)");
 static_assert(sizeof(bh_black_hole_uniform) == 132, "BlackHoleUniform is 132 bytes (blackhole.rs:37-51)");
 static_assert(sizeof(bh_ray_details) == 32, "RayDetails is 32 bytes (ray_pipeline.rs:3-14)");
-
-struct bh_ctx {
-    int device = 0;
-    int sm_count = 0;
-    uchar4 *tex[3] = { nullptr, nullptr, nullptr };
-    int tex_w[3] = { 0, 0, 0 }, tex_h[3] = { 0, 0, 0 };
-    unsigned char *models = nullptr;     // BH_MAX_MODELS * kModelStride
-    int models_uploaded = 0;
-    int numeric_mode = BH_NUMERIC_FUSED;
-};
-
-struct bh_ray_pipeline {
-    bh_ctx *ctx = nullptr;
-    uint32_t w = 0, h = 0;
-    const bh_ray_pipeline *prev = nullptr;
-    uint32_t band_rows = 0, rank = 0, n_ranks = 1, local_rows = 0;
-    float4 *own_out = nullptr;
-    size_t own_out_rows = 0;
-    float4 *bound_out = nullptr;
-    float4 *bound_frame = nullptr;                   // full-frame target (global row addressing), local or peer memory
-    int32_t *aux_hit = nullptr;
-    uint32_t *aux_steps = nullptr;
-    uint8_t *aux_class = nullptr;
-    uint32_t aux_mask = 0;
-    unsigned long long *stats = nullptr;
-    unsigned int *work = nullptr;
-    unsigned int *queue = nullptr;
-    cudaStream_t last_stream = nullptr;
-    bool ran = false;
-    cudaStream_t copy_stream = nullptr;              // chunked read-back (bh_ray_pipeline_pass_to_host)
-    cudaEvent_t chunk_done[16] = {};
-    cudaEvent_t copy_done = nullptr;
-    bool copy_pending = false;
-    float4 *out() const { return bound_frame ? bound_frame : (bound_out ? bound_out : own_out); }
-};
-
-struct bh_sky_pipeline {
-    bh_ctx *ctx = nullptr;
-    const bh_ray_pipeline *prev = nullptr;
-    bh_sky_format format = BH_SKY_RGBA16F;
-    void *own_out = nullptr;
-    void *bound_out = nullptr;
-    unsigned long long *stats = nullptr;
-    cudaStream_t last_stream = nullptr;
-    bool ran = false;
-    void *out() const { return bound_out ? bound_out : own_out; }
-    size_t texel_bytes() const { return format == BH_SKY_RGBA32F ? 16 : 8; }
-};
 
 static uint32_t count_local_rows(uint32_t h, uint32_t band_rows, uint32_t rank, uint32_t n_ranks)
 {
@@ -166,6 +112,7 @@ void bh_ctx_destroy(bh_ctx *ctx)
     cudaSetDevice(ctx->device);
     for (auto &t : ctx->tex) if (t) cudaFree(t);
     if (ctx->models) cudaFree(ctx->models);
+    if (ctx->async_err) cudaFreeHost(ctx->async_err);
     delete ctx;
 }
 
@@ -222,6 +169,9 @@ static int upload_models(bh_ctx *ctx, const void *bytes, size_t nbytes, bool asy
     const int count = (int)(nbytes / BH_MODEL_UNIFORM_SIZE);
     for (int i = 0; i < count; ++i) {
         const unsigned char *src = static_cast<const unsigned char *>(bytes) + (size_t)i * BH_MODEL_UNIFORM_SIZE;
+        // the kernel follows every index of the blob unchecked (the reference's WGSL clamps them, naga Restrict): refuse a
+        // malformed blob here.  The per-frame async re-send trusts its caller (bh_model_validate is exported for it).
+        if (!async) { const int vrc = bh_model_validate(src); if (vrc != BH_OK) return vrc; }
         if (async) BH_CUDA(cudaMemcpyAsync(ctx->models + (size_t)i * kModelStride, src, BH_MODEL_UNIFORM_SIZE, cudaMemcpyHostToDevice, stream));
         else BH_CUDA(cudaMemcpy(ctx->models + (size_t)i * kModelStride, src, BH_MODEL_UNIFORM_SIZE, cudaMemcpyHostToDevice));
     }
@@ -323,7 +273,9 @@ int bh_ray_pipeline_bind_output(bh_ray_pipeline *p, void *device_rgba32f)
     return BH_OK;
 }
 
-static int build_pass_params(bh_ray_pipeline *p, const bh_camera_uniform *camera, const bh_black_hole_uniform *black_hole,
+}  // extern "C"
+
+int bh::build_pass_params(bh_ray_pipeline *p, const bh_camera_uniform *camera, const bh_black_hole_uniform *black_hole,
                              const bh_ray_details *details, const char *who, PassParams &P)
 {
     if (!p || !camera || !black_hole || !details) { set_error("%s: NULL argument", who); return BH_ERR_INVALID; }
@@ -332,6 +284,10 @@ static int build_pass_params(bh_ray_pipeline *p, const bh_camera_uniform *camera
     if (details->model_count < 0 || details->model_count > c->models_uploaded) {
         set_error("%s: model_count=%d but %d model(s) uploaded", who, details->model_count, c->models_uploaded);
         return BH_ERR_INVALID;
+    }
+    if (p->prev && p->prev->host_only) {
+        set_error("%s: the previous level's last pass wrote its output to host memory only (bh_ray_pipeline_pass_to_host, n_chunks=0)", who);
+        return BH_ERR_STATE;
     }
     memset(&P, 0, sizeof P);
     P.cam = *camera; P.hole = *black_hole; P.det = *details;
@@ -360,6 +316,8 @@ static int build_pass_params(bh_ray_pipeline *p, const bh_camera_uniform *camera
     return BH_OK;
 }
 
+extern "C" {
+
 int bh_ray_pipeline_bind_frame(bh_ray_pipeline *p, void *device_frame_rgba32f)
 {
     if (!p || ((uintptr_t)device_frame_rgba32f & 15u)) { set_error("bh_ray_pipeline_bind_frame: pointer must be 16-byte aligned"); return BH_ERR_INVALID; }
@@ -374,9 +332,13 @@ int bh_shared_frame_create(bh_ctx *ctx, size_t nbytes, void **device_ptr, uint8_
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
     BH_CUDA(cudaSetDevice(ctx->device));
     void *ptr = nullptr;
-    BH_CUDA(cudaMalloc(&ptr, nbytes));
+    // the frame, then BH_SHARED_FLAGS 32-bit flags at the next 256-byte boundary (bh_shared_frame_flags), zeroed
+    const size_t flag_off = (nbytes + 255) / 256 * 256;
+    BH_CUDA(cudaMalloc(&ptr, flag_off + BH_SHARED_FLAGS * sizeof(uint32_t)));
+    cudaError_t e = cudaMemset(static_cast<unsigned char *>(ptr) + flag_off, 0, BH_SHARED_FLAGS * sizeof(uint32_t));
+    if (e != cudaSuccess) { cudaFree(ptr); return cuda_fail(e, "bh_shared_frame_create: cudaMemset"); }
     cudaIpcMemHandle_t h;
-    cudaError_t e = cudaIpcGetMemHandle(&h, ptr);
+    e = cudaIpcGetMemHandle(&h, ptr);
     if (e != cudaSuccess) { cudaFree(ptr); return cuda_fail(e, "cudaIpcGetMemHandle"); }
     memcpy(handle_out, &h, 64);
     *device_ptr = ptr;
@@ -412,7 +374,7 @@ int bh_ray_pipeline_pass(bh_ray_pipeline *p, const bh_camera_uniform *camera, co
     BH_CUDA(cudaSetDevice(c->device));
     cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
     LaunchConfig cfg{ c->sm_count, c->numeric_mode };
-    p->last_stream = stream; p->ran = true;
+    p->last_stream = stream; p->ran = true; p->host_only = false;
     if (p->local_rows == 0) return BH_OK;
     BH_CUDA(launch_ray_pass(P, cfg, stream));
     return BH_OK;
@@ -438,7 +400,7 @@ int bh_ray_pipeline_pass_to_host(bh_ray_pipeline *p, const bh_camera_uniform *ca
         if (e != cudaSuccess) { cudaGetLastError(); set_error("bh_ray_pipeline_pass_to_host: n_chunks=0 needs page-locked, mapped host memory (%s)", cudaGetErrorString(e)); return BH_ERR_INVALID; }
         P.out = static_cast<float4 *>(mapped);
         LaunchConfig cfg0{ c->sm_count, c->numeric_mode };
-        p->last_stream = stream; p->ran = true;
+        p->last_stream = stream; p->ran = true; p->host_only = true;
         if (p->local_rows == 0) return BH_OK;
         BH_CUDA(launch_ray_pass(P, cfg0, stream));
         return BH_OK;
@@ -449,7 +411,7 @@ int bh_ray_pipeline_pass_to_host(bh_ray_pipeline *p, const bh_camera_uniform *ca
         BH_CUDA(cudaEventCreateWithFlags(&p->copy_done, cudaEventDisableTiming));
     }
     LaunchConfig cfg{ c->sm_count, c->numeric_mode };
-    p->last_stream = stream; p->ran = true;
+    p->last_stream = stream; p->ran = true; p->host_only = false;
     if (p->local_rows == 0) return BH_OK;
     const size_t row_bytes = (size_t)p->w * sizeof(float4);
     if (P.prev != nullptr) n_chunks = 1;                 // fine levels: classification + queue cover the whole level at once
@@ -505,6 +467,7 @@ int bh_ray_pipeline_read(bh_ray_pipeline *p, float *host_rgba32f, int32_t *host_
         set_error("bh_ray_pipeline_read: aux buffer requested but not enabled (bh_ray_pipeline_enable_aux)");
         return BH_ERR_STATE;
     }
+    if (host_rgba32f && p->host_only) { set_error("bh_ray_pipeline_read: the last pass wrote its RGBA to host memory only (bh_ray_pipeline_pass_to_host, n_chunks=0)"); return BH_ERR_STATE; }
     if (host_rgba32f && p->bound_frame) { set_error("bh_ray_pipeline_read: output is bound to an external frame (bh_ray_pipeline_bind_frame); read the frame instead"); return BH_ERR_STATE; }
     BH_CUDA(cudaSetDevice(p->ctx->device));
     BH_CUDA(cudaStreamSynchronize(p->last_stream));
@@ -554,6 +517,29 @@ int bh_sky_pipeline_create(bh_ctx *ctx, const bh_ray_pipeline *prev, bh_sky_form
     return BH_OK;
 }
 
+int bh_sky_pipeline_create_for_frame(bh_ctx *ctx, const void *device_frame_rgba32f, uint32_t width, uint32_t height,
+                                     bh_sky_format format, bh_sky_pipeline **out)
+{
+    if (!out) { set_error("bh_sky_pipeline_create_for_frame: out is NULL"); return BH_ERR_INVALID; }
+    *out = nullptr;
+    if (!ctx || !device_frame_rgba32f || ((uintptr_t)device_frame_rgba32f & 15u) || width == 0 || height == 0 || width > 65535 ||
+        height > 65535 || ((int)format != 0 && (int)format != 1)) {
+        set_error("bh_sky_pipeline_create_for_frame: bad argument");
+        return BH_ERR_INVALID;
+    }
+    BH_CUDA(cudaSetDevice(ctx->device));
+    bh_sky_pipeline *s = new (std::nothrow) bh_sky_pipeline();
+    if (!s) { set_error("bh_sky_pipeline_create_for_frame: out of host memory"); return BH_ERR_NOMEM; }
+    s->ctx = ctx; s->format = format;
+    s->raw_prev = static_cast<const float4 *>(device_frame_rgba32f); s->raw_w = width; s->raw_h = height;
+    cudaError_t e = cudaMalloc(&s->own_out, (size_t)width * height * s->texel_bytes());
+    if (e == cudaSuccess) e = cudaMalloc(&s->stats, sizeof(unsigned long long) * kStatCount);
+    if (e == cudaSuccess) e = cudaMemset(s->stats, 0, sizeof(unsigned long long) * kStatCount);
+    if (e != cudaSuccess) { const int rc = cuda_fail(e, "bh_sky_pipeline_create_for_frame: cudaMalloc"); bh_sky_pipeline_destroy(s); return rc; }
+    *out = s;
+    return BH_OK;
+}
+
 void bh_sky_pipeline_destroy(bh_sky_pipeline *s)
 {
     if (!s) return;
@@ -576,14 +562,20 @@ int bh_sky_pipeline_pass(bh_sky_pipeline *s, void *cuda_stream)
     if (!s) { set_error("bh_sky_pipeline_pass: NULL pipeline"); return BH_ERR_INVALID; }
     bh_ctx *c = s->ctx;
     if (!c->tex[2]) { set_error("bh_sky_pipeline_pass: sky texture not set"); return BH_ERR_STATE; }
+    if (s->prev && s->prev->host_only) { set_error("bh_sky_pipeline_pass: the ray level's last pass wrote its output to host memory only (pass_to_host, n_chunks=0)"); return BH_ERR_STATE; }
+    if (s->prev && s->prev->bound_frame && s->prev->n_ranks > 1) {
+        // prev->out() is then a whole (possibly remote) frame addressed by global row, not this rank's bands
+        set_error("bh_sky_pipeline_pass: the ray level renders tiled into a bound frame; resolve the assembled frame instead (bh_frame_multi does)");
+        return BH_ERR_STATE;
+    }
     BH_CUDA(cudaSetDevice(c->device));
     cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
     SkyParams S;
     memset(&S, 0, sizeof S);
     S.sky = DevTexture{ c->tex[2], c->tex_w[2], c->tex_h[2] };
-    S.prev = s->prev->out();
+    S.prev = s->prev ? s->prev->out() : s->raw_prev;
     S.out = s->out();
-    S.n_pixels = (int)((size_t)s->prev->local_rows * s->prev->w);
+    S.n_pixels = (int)s->pixels();
     S.format = (int)s->format;
     S.stats = s->stats;
     s->last_stream = stream; s->ran = true;
@@ -600,9 +592,10 @@ int bh_sky_pipeline_read(bh_sky_pipeline *s, void *host_rgba)
 {
     if (!s || !host_rgba) { set_error("bh_sky_pipeline_read: NULL argument"); return BH_ERR_INVALID; }
     if (!s->ran) { set_error("bh_sky_pipeline_read: no pass has been enqueued"); return BH_ERR_STATE; }
+    if (s->prev && s->prev->bound_frame && s->prev->n_ranks > 1) { set_error("bh_sky_pipeline_read: the ray level renders tiled into a bound frame"); return BH_ERR_STATE; }
     BH_CUDA(cudaSetDevice(s->ctx->device));
     BH_CUDA(cudaStreamSynchronize(s->last_stream));
-    BH_CUDA(cudaMemcpy(host_rgba, s->out(), (size_t)s->prev->local_rows * s->prev->w * s->texel_bytes(), cudaMemcpyDeviceToHost));
+    BH_CUDA(cudaMemcpy(host_rgba, s->out(), s->pixels() * s->texel_bytes(), cudaMemcpyDeviceToHost));
     return BH_OK;
 }
 

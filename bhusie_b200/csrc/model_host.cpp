@@ -160,6 +160,49 @@ const char *skip_ws(const char *p) { while (*p == ' ' || *p == '\t') ++p; return
 
 }  // namespace
 
+// Walks the BVH of a ModelUniform blob from its root the way trace_ray_model (ray.wgsl:287-363) can reach it and checks
+// every index the kernel would follow: children inside the node array and numbered after their parent (which makes the
+// traversal finite), leaf ranges inside bvh_lookup, lookup entries inside the triangle array, point / normal indices inside
+// their arrays.  The reference's WGSL clamps out-of-range indices (naga Restrict); this library refuses the blob instead.
+extern "C" int bh_model_validate(const void *model_uniform)
+{
+    if (!model_uniform) { bh::set_error("bh_model_validate: null argument"); return BH_ERR_INVALID; }
+    ModelView m(const_cast<void *>(model_uniform));
+    constexpr int32_t kMax = BH_MAX_MODEL_VERTICES;
+    // an empty model (Model::new + build_bvh over 0 triangles, triangle.rs:143-157) has root = {left_child 0, obj_count 0}: the
+    // shader reads it as an inner node whose children are nodes 0 and 1; node 0 then carries the builder's empty bounds
+    // (min = f32::MAX, max = f32::MIN, triangle.rs:160-161), which no ray hits, so the traversal ends at once — kept as is
+    if (m.nodes[0].obj_count == 0 && m.nodes[0].left_child == 0 && m.nodes[0].mn[0] > m.nodes[0].mx[0]) return BH_OK;
+    std::vector<int32_t> todo;
+    todo.push_back(0);
+    size_t visited = 0;
+    while (!todo.empty()) {
+        const int32_t ni = todo.back();
+        todo.pop_back();
+        if (++visited > static_cast<size_t>(kMax)) { bh::set_error("bh_model_validate: BVH has more reachable nodes than the node array"); return BH_ERR_INVALID; }
+        const NodeU &node = m.nodes[ni];
+        if (node.obj_count == 0) {
+            const int32_t c = node.left_child;
+            if (c <= ni || c < 0 || c > kMax - 2) { bh::set_error("bh_model_validate: node %d has children %d,%d (must follow their parent inside the array)", ni, c, c + 1); return BH_ERR_INVALID; }
+            todo.push_back(c + 1);
+            todo.push_back(c);
+        } else {
+            if (node.obj_count < 0 || node.left_child < 0 || node.left_child > kMax - node.obj_count) {
+                bh::set_error("bh_model_validate: leaf %d covers bvh_lookup[%d..+%d)", ni, node.left_child, node.obj_count);
+                return BH_ERR_INVALID;
+            }
+            for (int32_t k = 0; k < node.obj_count; ++k) {
+                const int32_t ti = m.lookup[node.left_child + k];
+                if (ti < 0 || ti >= kMax) { bh::set_error("bh_model_validate: bvh_lookup[%d] = %d", node.left_child + k, ti); return BH_ERR_INVALID; }
+                const TriU &t = m.tris[ti];
+                for (int32_t idx : { t.p1, t.p2, t.p3, t.n1, t.n2, t.n3 })
+                    if (idx < 0 || idx >= kMax) { bh::set_error("bh_model_validate: triangle %d has index %d", ti, idx); return BH_ERR_INVALID; }
+            }
+        }
+    }
+    return BH_OK;
+}
+
 extern "C" int bh_model_build_bvh(void *model_uniform, int32_t triangle_count, bh_model_info *info)
 {
     if (info) std::memset(info, 0, sizeof *info);
@@ -319,6 +362,15 @@ extern "C" int bh_model_load_obj(const char *path, void *model_uniform, bh_model
                 float *dst = m.normals + 4 * static_cast<size_t>(normal_count);
                 dst[0] = cr[0] * inv; dst[1] = cr[1] * inv; dst[2] = cr[2] * inv;
                 ln[0] = ln[1] = ln[2] = normal_count++;
+            }
+            // Q17: mesh_offset is a TRIANGLE count added to POINT indices; on multi-object files the sum can leave the
+            // 524288-slot arrays, where the reference shader would clamp (naga Restrict) and this kernel would read out of
+            // bounds — refuse instead
+            for (int k = 0; k < 3; ++k) {
+                if (lp[k] + mesh_offset >= BH_MAX_MODEL_VERTICES || ln[k] + normal_offset >= BH_MAX_MODEL_VERTICES) {
+                    bh::set_error("bh_model_load_obj: offset index beyond MAX_MODEL_VERTICES (multi-object OBJ, model.rs:22,71-73)");
+                    return BH_ERR_TOOBIG;
+                }
             }
             m.tris[triangle_count++] = TriU{ lp[0] + mesh_offset, lp[1] + mesh_offset, lp[2] + mesh_offset,
                                              ln[0] + normal_offset, ln[1] + normal_offset, ln[2] + normal_offset };

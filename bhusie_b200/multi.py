@@ -13,8 +13,14 @@ Two exchanges are implemented:
   "p2p"   (default when CUDA IPC is available) rank 0 owns the frame and exports it with CUDA IPC; every other rank
           maps it and its ray kernel stores finished pixels STRAIGHT into rank 0's memory at their global row
           (bh_ray_pipeline_bind_frame) — 16-byte stores over NVLink while the warp keeps tracing, so the exchange is
-          fused into the pass and overlaps it completely.  One 4-byte all-reduce per frame orders "all ranks done"
-          before rank 0 consumes the frame.
+          fused into the pass and overlaps it completely.  Ordering needs no collective either: after its kernel a rank
+          stores the frame number into its flag behind the frame (bh_stream_signal), rank 0 waits on the device until
+          all flags reached it (bh_stream_wait), and the same pair tells the writers that rank 0 has consumed a frame.
+
+With `pyramid=` the frame is the reference's adaptive grid (mod.rs:170-216): the coarse levels are replicated on every
+rank (12.5 % of the pixels, no halo exchange), the last level is tiled, and rank 0 resolves the sky over the assembled frame.
+`HostTiledFrame` is the end-to-end variant: every rank stores its bands straight into ONE page-locked host frame in POSIX
+shared memory over its own PCIe link.
 """
 from __future__ import annotations
 
@@ -87,29 +93,47 @@ class _DevicePointer:
         self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (ptr, False), "version": 2, "strides": None}
 
 
-class TiledFrame:
-    """One frame of the single-level ray pass on `world` ranks: RayPipeline with cyclic-band tiling, exchanged
-    either by NCCL gather ("nccl") or by direct peer stores into rank 0's frame ("p2p")."""
+CONSUMED_SLOT = 48          # flag rank 0 bumps when it has finished reading a frame (ranks use slots 0..world-1)
+WAIT_TIMEOUT_MS = 20000
 
-    def __init__(self, ctx, width: int, height: int, rank: int = 0, world: int = 1, band_rows: int = 8, aux: int = 0,
-                 exchange: str = "p2p"):
+
+class TiledFrame:
+    """One frame of the ray pass on `world` ranks: RayPipeline(s) with cyclic-band tiling of the last level, exchanged
+    either by NCCL gather ("nccl") or by direct peer stores into rank 0's frame ("p2p").
+
+    pyramid=None: single level width x height, every pixel traced.  pyramid=dict(base=(72, 41), multiplier=3, iters=4,
+    sky_format=...): the reference's adaptive grid; width/height are then the last level's."""
+
+    def __init__(self, ctx, width: int = 0, height: int = 0, rank: int = 0, world: int = 1, band_rows: int = 8, aux: int = 0,
+                 exchange: str = "p2p", pyramid: "dict | None" = None):
         import torch
-        from .pipelines import RayPipeline
+        from .pipelines import RayPipeline, SkyPipeline
+        from .uniforms import pyramid_levels
 
         if exchange not in ("p2p", "nccl"):
             raise ValueError("exchange must be 'p2p' or 'nccl'")
         self.ctx = ctx
         self.exchange = exchange if world > 1 else "none"
+        sizes = [(width, height)]
+        sky_format = None
+        if pyramid is not None:
+            sizes = pyramid_levels(pyramid.get("base", (72, 41)), pyramid.get("multiplier", 3), pyramid.get("iters", 4))
+            sky_format = pyramid.get("sky_format")
+            width, height = sizes[-1]
         self.rank, self.world, self.width, self.height = rank, world, width, height
         self.band_rows = band_rows if world > 1 else height
         self.layout = BandLayout(height, self.band_rows, world)
-        self.pipeline = RayPipeline(ctx, width, height, aux=aux)
+        self.levels = []
+        for (w, h) in sizes:
+            self.levels.append(RayPipeline(ctx, w, h, self.levels[-1] if self.levels else None, aux=aux))
+        self.pipeline = self.levels[-1]                      # the tiled level
         if world > 1:
             self.pipeline.set_tiling(self.band_rows, rank, world)
         assert self.pipeline.local_rows == self.layout.local_rows(rank)
         dev = torch.device("cuda", ctx.device)
-        self.frame = self.staging = self.row_index = self.local = None
-        self._shared_ptr = 0
+        self.frame = self.staging = self.row_index = self.local = self.sky = None
+        self._shared_ptr = self._flags = 0
+        self._seq = 0
         if self.exchange == "p2p":
             import torch.distributed as dist
             nbytes = height * width * 16
@@ -118,53 +142,144 @@ class TiledFrame:
                 h = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
             else:
                 h = torch.empty(64, dtype=torch.uint8, device=dev)
-            dist.broadcast(h, 0)
+            dist.broadcast(h, 0)                             # set-up only: the handle has to reach the other processes once
             if rank != 0:
                 self._shared_ptr = ctx.shared_frame_open(bytes(h.cpu().tolist()))
+            self._flags = ctx.shared_frame_flags(self._shared_ptr, nbytes)
             self.pipeline.bind_frame(self._shared_ptr)
-            self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
             if rank == 0:
                 self.frame = torch.as_tensor(_DevicePointer(self._shared_ptr, (height, width, 4)), device=dev)
-            return
-        self.local = torch.zeros((self.layout.max_local_rows, width, 4), dtype=torch.float32, device=dev)
-        self.pipeline.bind_output(self.local.data_ptr())
-        if rank == 0 and world > 1:
-            self.frame = torch.zeros((height, width, 4), dtype=torch.float32, device=dev)
-            self.staging = torch.empty((world,) + tuple(self.local.shape), dtype=torch.float32, device=dev)
-            if not self.layout.uniform:
-                self.row_index = [torch.as_tensor(self.layout.rows_of(r), device=dev) for r in range(world)]
+        else:
+            self.local = torch.zeros((self.layout.max_local_rows, width, 4), dtype=torch.float32, device=dev)
+            self.pipeline.bind_output(self.local.data_ptr())
+            if rank == 0 and world > 1:
+                self.frame = torch.zeros((height, width, 4), dtype=torch.float32, device=dev)
+                self.staging = torch.empty((world,) + tuple(self.local.shape), dtype=torch.float32, device=dev)
+                if not self.layout.uniform:
+                    self.row_index = [torch.as_tensor(self.layout.rows_of(r), device=dev) for r in range(world)]
+        if sky_format is not None and rank == 0:
+            t = self.frame_tensor()
+            self.sky = SkyPipeline(ctx, None, sky_format, frame=(t.data_ptr(), width, height))
 
     def render_local(self, camera, black_hole, details, stream=None):
-        self.pipeline.pass_(camera, black_hole, details, stream)
+        """Enqueues this rank's share on `stream`: the replicated coarse levels, then its bands of the last level."""
+        self._seq += 1
+        if self.exchange == "p2p" and self.rank != 0 and self._seq > 1:
+            # this rank's kernel writes into rank 0's frame: not before rank 0 has consumed the previous one
+            self.ctx.stream_wait(self._flags + 4 * CONSUMED_SLOT, 1, self._seq - 1, WAIT_TIMEOUT_MS, stream)
+        for rp in self.levels:
+            rp.pass_(camera, black_hole, details, stream)
+        if self.exchange == "p2p" and self.rank != 0:
+            self.ctx.stream_signal(self._flags + 4 * self.rank, self._seq, stream)
 
     def gather(self, stream=None):
-        """After this (stream-ordered) rank 0's frame holds every rank's rows."""
+        """After this (stream-ordered on `stream`) rank 0's frame holds every rank's rows of the frame just rendered."""
         if self.exchange == "p2p":
-            import torch.distributed as dist
-            dist.all_reduce(self._flag)          # 4 bytes: completes on a rank only after every rank's kernel has finished
+            if self.rank == 0:
+                self.ctx.stream_wait(self._flags + 4, self.world - 1, self._seq, WAIT_TIMEOUT_MS, stream)
         elif self.world > 1:
-            gather_bands(self.local, self.layout, self.rank, self.frame, self.staging, self.row_index)
+            import torch
+            ts = _torch_stream(stream, self.ctx.device)
+            with torch.cuda.stream(ts):                       # the collective runs on the stream the kernels were enqueued on
+                gather_bands(self.local, self.layout, self.rank, self.frame, self.staging, self.row_index)
+
+    def resolve_sky(self, stream=None):
+        """Rank 0, pyramid mode: the sky resolve over the assembled frame (sky.wgsl, after the gather)."""
+        if self.sky is not None:
+            self.sky.pass_(stream)
 
     def consumed(self, stream=None):
-        """Call (on every rank) after rank 0 has finished reading the frame and before the next render: in p2p mode the
-        other ranks write into rank 0's memory, so they must not start the next frame while it is still being read."""
-        if self.exchange == "p2p":
-            import torch.distributed as dist
-            dist.all_reduce(self._flag)
+        """Call (on every rank) after rank 0 has finished reading the frame (stream-ordered) and before the next render: in
+        p2p mode the other ranks write into rank 0's memory, so they must not start the next frame while it is being read."""
+        if self.exchange == "p2p" and self.rank == 0:
+            self.ctx.stream_signal(self._flags + 4 * CONSUMED_SLOT, self._seq, stream)
 
     def close(self):
+        if self.sky is not None:
+            self.sky.close()
+            self.sky = None
         self.pipeline.bind_frame(None)
         if self._shared_ptr:
             import torch
+            import torch.distributed as dist
             torch.cuda.synchronize()
+            if dist.is_initialized():
+                dist.barrier()                               # nobody unmaps / frees while a peer may still touch the frame
             self.frame = None
             self.ctx.shared_frame_release(self._shared_ptr, owner=self.rank == 0)
             self._shared_ptr = 0
+        for rp in reversed(self.levels):
+            rp.close()
+        self.levels = []
 
     def render(self, camera, black_hole, details, stream=None):
         self.render_local(camera, black_hole, details, stream)
         self.gather(stream)
+        self.resolve_sky(stream)
 
     def frame_tensor(self):
         """Rank 0: the assembled (H, W, 4) RGBA32F frame on the device."""
         return self.local[: self.height] if self.world == 1 else self.frame
+
+
+def _torch_stream(stream, device: int):
+    import torch
+    if stream is None:
+        return torch.cuda.current_stream(device)
+    if hasattr(stream, "cuda_stream"):
+        return stream
+    return torch.cuda.ExternalStream(int(stream), device=device)
+
+
+class HostTiledFrame:
+    """End-to-end frame on `world` ranks with HOST buffers: one page-locked frame in POSIX shared memory that every rank
+    maps (bh_host_frame); each rank's ray kernel stores its cyclic bands straight into it over its own PCIe link — no
+    NVLink hop, no D2H copy, all links busy at once.  Ordering is host-side flags in the same segment."""
+
+    def __init__(self, ctx, width: int, height: int, rank: int, world: int, band_rows: int = 8, name: "str | None" = None):
+        import os
+        from .pipelines import HostFrame, RayPipeline
+        self.ctx, self.rank, self.world, self.width, self.height = ctx, rank, world, width, height
+        self.band_rows = band_rows if world > 1 else height
+        self.pipeline = RayPipeline(ctx, width, height)
+        if world > 1:
+            self.pipeline.set_tiling(self.band_rows, rank, world)
+        self.name = name or f"/bhframe_{os.environ.get('MASTER_PORT', '0')}_{width}x{height}"
+        nbytes = width * height * 16
+        if world > 1:
+            import torch.distributed as dist
+            if rank == 0:
+                self.host = HostFrame(ctx, self.name, nbytes, create=True)
+            dist.barrier()
+            if rank != 0:
+                self.host = HostFrame(ctx, self.name, nbytes, create=False)
+            dist.barrier()
+        else:
+            self.host = HostFrame(ctx, self.name, nbytes, create=True)
+        self._seq = 0
+
+    def render(self, camera, black_hole, details, stream=None):
+        """Every rank: enqueue, wait for the own kernel, publish.  Rank 0 returns once the whole frame is in host memory."""
+        self._seq += 1
+        if self.rank != 0 and self._seq > 1:
+            self.host.wait(CONSUMED_SLOT, 1, self._seq - 1, WAIT_TIMEOUT_MS)        # rank 0 still reads the previous frame
+        self.pipeline.pass_to_host_frame(camera, black_hole, details, self.host.ptr, stream)
+        self.pipeline.sync()
+        self.host.signal(self.rank, self._seq)
+        if self.rank == 0 and self.world > 1:
+            self.host.wait(1, self.world - 1, self._seq, WAIT_TIMEOUT_MS)
+
+    def consumed(self):
+        if self.rank == 0:
+            self.host.signal(CONSUMED_SLOT, self._seq)
+
+    def frame_array(self) -> np.ndarray:
+        return self.host.array((self.height, self.width, 4))
+
+    def close(self):
+        self.pipeline.close()
+        if self.world > 1:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.barrier()
+        self.host.close()

@@ -124,6 +124,22 @@ class Context:
     def shared_frame_release(self, ptr: int, owner: bool):
         _lib.check(self._lib.bh_shared_frame_release(self._h, C.c_void_p(ptr), 1 if owner else 0))
 
+    def shared_frame_flags(self, ptr: int, nbytes: int) -> int:
+        """Device pointer of the BH_SHARED_FLAGS 32-bit flags that follow a shared frame of `nbytes` bytes."""
+        return int(self._lib.bh_shared_frame_flags(C.c_void_p(ptr), nbytes) or 0)
+
+    def stream_signal(self, flag_ptr: int, value: int, stream=None):
+        """Stream-ordered `*flag = value` (release, system scope): everything enqueued before it on `stream` is visible first."""
+        _lib.check(self._lib.bh_stream_signal(self._h, C.c_void_p(flag_ptr), value & 0xFFFFFFFF, _stream_ptr(stream)))
+
+    def stream_wait(self, flags_ptr: int, n_flags: int, value: int, timeout_ms: int = 10000, stream=None):
+        """Stream-ordered wait (on the device) until all `n_flags` flags have reached `value`; gives up after timeout_ms."""
+        _lib.check(self._lib.bh_stream_wait(self._h, C.c_void_p(flags_ptr), n_flags, value & 0xFFFFFFFF, timeout_ms, _stream_ptr(stream)))
+
+    def check_async(self):
+        """Raises BhError(-110) if a stream_wait on this context has given up since the last call."""
+        _lib.check(self._lib.bh_ctx_check_async(self._h))
+
     def math_probe(self, fn: str, a: np.ndarray, b: np.ndarray | None = None) -> np.ndarray:
         codes = {"pow": 0, "pow5": 1, "pow4": 2, "sin": 3, "cos": 4, "tan": 5, "atan2": 6, "acos": 7}
         a = np.ascontiguousarray(a, dtype=np.float32)
@@ -198,6 +214,13 @@ class RayPipeline:
         det = _bytes(details, RAY_DETAILS_SIZE)
         _lib.check(self._lib.bh_ray_pipeline_pass_to_host(self._h, cam, hole, det, C.c_void_p(host_ptr), n_chunks, _stream_ptr(stream)))
 
+    def pass_to_host_frame(self, camera, black_hole, details, host_ptr: int, stream=None):
+        """pass_() with this (tiled) pipeline's rows stored at their GLOBAL row into a full page-locked host frame (async)."""
+        cam = _bytes(camera, CAMERA_UNIFORM_SIZE)
+        hole = _bytes(black_hole, BLACK_HOLE_UNIFORM_SIZE)
+        det = _bytes(details, RAY_DETAILS_SIZE)
+        _lib.check(self._lib.bh_ray_pipeline_pass_to_host_frame(self._h, cam, hole, det, C.c_void_p(host_ptr), _stream_ptr(stream)))
+
     def sync(self):
         _lib.check(self._lib.bh_ray_pipeline_sync(self._h))
 
@@ -231,11 +254,19 @@ class RayPipeline:
 class SkyPipeline:
     """SkyPipeline::new (sky_pipeline.rs:18): resolves alpha==0 pixels of `prev` against the sky map."""
 
-    def __init__(self, ctx: Context, prev: RayPipeline, fmt: int = SKY_RGBA16F):
+    def __init__(self, ctx: Context, prev: "RayPipeline | None", fmt: int = SKY_RGBA16F, frame: "tuple | None" = None):
+        """`prev`: the ray level to resolve; or `frame=(device_ptr, width, height)`: a raw RGBA32F frame in device memory
+        (the frame a multi-GPU render assembles)."""
         self._lib = ctx._lib
         self.ctx, self.prev, self.fmt = ctx, prev, fmt
         h = C.c_void_p()
-        _lib.check(self._lib.bh_sky_pipeline_create(ctx._h, prev._h, fmt, C.byref(h)))
+        if frame is not None:
+            ptr, w, hh = frame
+            _lib.check(self._lib.bh_sky_pipeline_create_for_frame(ctx._h, C.c_void_p(ptr), w, hh, fmt, C.byref(h)))
+            self._shape = (int(hh), int(w))
+        else:
+            _lib.check(self._lib.bh_sky_pipeline_create(ctx._h, prev._h, fmt, C.byref(h)))
+            self._shape = None
         self._h = h
 
     def close(self):
@@ -260,7 +291,7 @@ class SkyPipeline:
         _lib.check(self._lib.bh_sky_pipeline_pass(self._h, _stream_ptr(stream)))
 
     def read(self) -> np.ndarray:
-        rows, w = self.prev.local_rows, self.prev.width
+        rows, w = self._shape if self._shape else (self.prev.local_rows, self.prev.width)
         out = np.empty((rows, w, 4), np.float32 if self.fmt == SKY_RGBA32F else np.float16)
         _lib.check(self._lib.bh_sky_pipeline_read(self._h, out.ctypes.data_as(C.c_void_p)))
         return out
@@ -291,6 +322,118 @@ class RayPyramid:
             rp.close()
 
 
+class FrameMulti:
+    """bh_frame_multi: the whole compute pass of Renderer::render (mod.rs:406-421) on N devices driven from ONE host
+    thread of ONE process — coarse pyramid levels replicated per device, the last level tiled in cyclic row bands whose
+    pixels every device stores straight into device 0's frame over NVLink, sky resolve on device 0.  No torch, no NCCL."""
+
+    def __init__(self, ctxs: "list[Context]", base=(72, 41), multiplier: int = 3, iters: int = 4, band_rows: int = 8,
+                 sky_format: "int | None" = SKY_RGBA16F):
+        self._lib = ctxs[0]._lib
+        self.ctxs = list(ctxs)
+        self.sky_format = sky_format
+        arr = (C.c_void_p * len(ctxs))(*[c._h for c in ctxs])
+        desc = _lib.FrameMultiDesc(int(base[0]), int(base[1]), int(iters), int(multiplier), int(band_rows),
+                                   -1 if sky_format is None else int(sky_format))
+        h = C.c_void_p()
+        _lib.check(self._lib.bh_frame_multi_create(arr, len(ctxs), C.byref(desc), C.byref(h)))
+        self._h = h
+        self.width = int(self._lib.bh_frame_multi_width(h))
+        self.height = int(self._lib.bh_frame_multi_height(h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.bh_frame_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def pass_(self, camera, black_hole, details):
+        _lib.check(self._lib.bh_frame_multi_pass(self._h, _bytes(camera, CAMERA_UNIFORM_SIZE), _bytes(black_hole, BLACK_HOLE_UNIFORM_SIZE),
+                                                 _bytes(details, RAY_DETAILS_SIZE)))
+
+    def pass_to_host(self, camera, black_hole, details, host_ptr: int):
+        _lib.check(self._lib.bh_frame_multi_pass_to_host(self._h, _bytes(camera, CAMERA_UNIFORM_SIZE), _bytes(black_hole, BLACK_HOLE_UNIFORM_SIZE),
+                                                         _bytes(details, RAY_DETAILS_SIZE), C.c_void_p(host_ptr)))
+
+    def sync(self):
+        _lib.check(self._lib.bh_frame_multi_sync(self._h))
+
+    @property
+    def output_ptr(self) -> int:
+        return int(self._lib.bh_frame_multi_output(self._h) or 0)
+
+    @property
+    def sky_output_ptr(self) -> int:
+        return int(self._lib.bh_frame_multi_sky_output(self._h) or 0)
+
+    def read(self, rgba: bool = True, sky: bool = True) -> dict:
+        out = {}
+        if rgba:
+            out["rgba"] = np.empty((self.height, self.width, 4), np.float32)
+        if sky and self.sky_format is not None:
+            out["sky"] = np.empty((self.height, self.width, 4), np.float32 if self.sky_format == SKY_RGBA32F else np.float16)
+        p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        _lib.check(self._lib.bh_frame_multi_read(self._h, p(out.get("rgba")), p(out.get("sky"))))
+        return out
+
+    def stats(self, strict: bool = True) -> dict:
+        s = _lib.PassStats()
+        ms = C.c_float(0.0)
+        rc = self._lib.bh_frame_multi_stats(self._h, C.byref(s), C.byref(ms))
+        if rc != 0 and (strict or rc != -34):
+            _lib.check(rc)
+        d = s.as_dict()
+        d["elapsed_ms"] = float(ms.value)
+        return d
+
+
+class HostFrame:
+    """bh_host_frame: a page-locked frame in POSIX shared memory that every rank of a node maps and registers with CUDA, so
+    each rank's kernel stores its bands straight into the caller's host frame over its own PCIe link."""
+
+    def __init__(self, ctx: Context, name: str, nbytes: int, create: bool):
+        self._lib = ctx._lib
+        self.ctx, self.name, self.nbytes, self.owner = ctx, name, int(nbytes), bool(create)
+        h = C.c_void_p()
+        _lib.check(self._lib.bh_host_frame_create(ctx._h, name.encode(), self.nbytes, 1 if create else 0, C.byref(h)))
+        self._h = h
+        self.ptr = int(self._lib.bh_host_frame_ptr(h))
+
+    def array(self, shape, dtype=np.float32) -> np.ndarray:
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        assert n <= self.nbytes
+        buf = (C.c_uint8 * n).from_address(self.ptr)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def signal(self, slot: int, value: int):
+        _lib.check(self._lib.bh_host_frame_signal(self._h, slot, value & 0xFFFFFFFF))
+
+    def wait(self, first_slot: int, n_slots: int, value: int, timeout_ms: int = 10000):
+        _lib.check(self._lib.bh_host_frame_wait(self._h, first_slot, n_slots, value & 0xFFFFFFFF, timeout_ms))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.bh_host_frame_destroy(self._h, 1 if self.owner else 0)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def validate_model(blob: np.ndarray):
+    """bh_model_validate: raises BhError(-22) when the BVH of a ModelUniform blob leads the traversal out of its arrays."""
+    a = np.ascontiguousarray(blob, dtype=np.uint8).reshape(-1)
+    _lib.check(_lib.load().bh_model_validate(a.ctypes.data_as(C.c_void_p)))
+
+
 def load_obj_model(path: str) -> tuple[np.ndarray, dict]:
     """load_model (model.rs:7-87) + build_bvh through the library's host code -> ModelUniform bytes."""
     lib = _lib.load()
@@ -315,6 +458,6 @@ def model_from_arrays(points: np.ndarray, normals: np.ndarray, tris: np.ndarray,
     return blob, info.as_dict()
 
 
-__all__ = ["Context", "RayPipeline", "SkyPipeline", "RayPyramid", "Camera", "BlackHole", "RayDetails",
+__all__ = ["Context", "RayPipeline", "SkyPipeline", "RayPyramid", "FrameMulti", "HostFrame", "validate_model", "Camera", "BlackHole", "RayDetails",
            "load_obj_model", "model_from_arrays", "TEX_COLOR", "TEX_DISK", "TEX_SKY", "AUX_HIT", "AUX_STEPS",
            "AUX_CLASS", "SKY_RGBA16F", "SKY_RGBA32F", "NUMERIC_LITERAL", "NUMERIC_FUSED", "ORACLE_FLAVOUR_OF_MODE"]

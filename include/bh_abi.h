@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BH_ABI_VERSION 1
+#define BH_ABI_VERSION 2
 
 /* error codes (negative errno values) */
 #define BH_OK            0
@@ -43,6 +43,7 @@ extern "C" {
 #define BH_ERR_NOENT    (-2)    /* ENOENT: file not found */
 #define BH_ERR_TOOBIG   (-7)    /* E2BIG:  mesh exceeds MAX_MODEL_VERTICES */
 #define BH_ERR_NUMERIC  (-34)   /* ERANGE: the RK accept loop of ray.wgsl:425-451 would not terminate (e_max > 1) */
+#define BH_ERR_TIMEOUT  (-110)  /* ETIMEDOUT: a cross-GPU / cross-process wait gave up (a peer never signalled) */
 
 /* ---- uniform byte layouts (verbatim) ------------------------------------ */
 
@@ -204,11 +205,81 @@ typedef enum bh_sky_format {
     BH_SKY_RGBA32F = 1                      /* the value before the f16 store (parity) */
 } bh_sky_format;
 int  bh_sky_pipeline_create(bh_ctx *ctx, const bh_ray_pipeline *prev, bh_sky_format format, bh_sky_pipeline **out);
+/* Same pass over a raw width x height RGBA32F frame in device memory instead of a pipeline's output — the frame a
+ * multi-GPU render assembles on one device (bh_ray_pipeline_bind_frame). */
+int  bh_sky_pipeline_create_for_frame(bh_ctx *ctx, const void *device_frame_rgba32f, uint32_t width, uint32_t height,
+                                      bh_sky_format format, bh_sky_pipeline **out);
 void bh_sky_pipeline_destroy(bh_sky_pipeline *p);
 int  bh_sky_pipeline_bind_output(bh_sky_pipeline *p, void *device_rgba);
 int  bh_sky_pipeline_pass(bh_sky_pipeline *p, void *cuda_stream);
 const void *bh_sky_pipeline_output(const bh_sky_pipeline *p);
 int  bh_sky_pipeline_read(bh_sky_pipeline *p, void *host_rgba);   /* local_rows*width*(8|16) B */
+
+/* ---- multi-GPU (no reference counterpart: bhusie is single-GPU) ----------------------------------------
+ * Pixels of a level are independent (ray.wgsl:167-243), so the frame is cut into cyclic row bands, band b -> device
+ * b mod N; the scene is replicated; the coarse levels of the adaptive grid (12.5 % of the pixels) are replicated too, the
+ * last level is tiled, and every device's ray kernel stores its finished pixels straight into ONE frame on device 0 over
+ * NVLink (peer stores, fused into the pass).  The sky resolve then runs on device 0 over the assembled frame.
+ *
+ * (1) bh_frame_multi: one process, ONE host thread, N devices — what a Rust host like bhusie's (one thread,
+ *     src/app.rs:108-114) can drive.  No torch, no NCCL: peer access + CUDA events.  `ctxs` are N contexts on N distinct
+ *     devices, each with the same textures / models uploaded by the caller; ctxs[0] owns the frame. */
+typedef struct bh_frame_multi bh_frame_multi;
+typedef struct bh_frame_multi_desc {
+    uint32_t base_width, base_height;       /* level 0 (levels == 1: the frame itself) */
+    uint32_t levels;                        /* 1 = single level, every pixel traced; n = the reference's adaptive grid, */
+    uint32_t multiplier;                    /*     S_k = multiplier*S_(k-1) - (multiplier-1)  (mod.rs:177-206: base 72x41, x3, 4 levels) */
+    uint32_t band_rows;                     /* rows per cyclic band of the last level (8 is a good default) */
+    int32_t  sky_format;                    /* -1: no sky resolve; else bh_sky_format: resolve the assembled frame on ctxs[0] */
+} bh_frame_multi_desc;
+int  bh_frame_multi_create(bh_ctx *const *ctxs, uint32_t n_devices, const bh_frame_multi_desc *desc, bh_frame_multi **out);
+void bh_frame_multi_destroy(bh_frame_multi *fm);
+uint32_t bh_frame_multi_width(const bh_frame_multi *fm);       /* final level */
+uint32_t bh_frame_multi_height(const bh_frame_multi *fm);
+/* Renderer::render's compute pass (mod.rs:406-421) on N devices: enqueue every level on every device (the object's own
+ * streams), join on device 0, resolve the sky there.  Asynchronous; a later pass waits for the previous frame's consumers. */
+int  bh_frame_multi_pass(bh_frame_multi *fm, const bh_camera_uniform *camera, const bh_black_hole_uniform *black_hole,
+                         const bh_ray_details *details);
+/* Same, but the LAST level's pixels are stored by each device straight into `pinned_host_rgba32f` (width*height*16 B of
+ * page-locked, mapped, portable memory) over that device's own PCIe link; no device frame, no sky resolve. */
+int  bh_frame_multi_pass_to_host(bh_frame_multi *fm, const bh_camera_uniform *camera, const bh_black_hole_uniform *black_hole,
+                                 const bh_ray_details *details, float *pinned_host_rgba32f);
+int  bh_frame_multi_sync(bh_frame_multi *fm);
+const float *bh_frame_multi_output(const bh_frame_multi *fm);      /* device 0: assembled RGBA32F frame of the last level */
+const void  *bh_frame_multi_sky_output(const bh_frame_multi *fm);  /* device 0: resolved frame (NULL when sky_format < 0) */
+int  bh_frame_multi_read(bh_frame_multi *fm, float *host_rgba32f, void *host_sky);     /* sync; both nullable */
+/* totals of the last frame: coarse levels counted once (device 0's copy), last level summed over the devices;
+ * *elapsed_ms (nullable) = device time of the frame from its first launch on device 0 to the end of the join / sky */
+int  bh_frame_multi_stats(bh_frame_multi *fm, bh_pass_stats *out, float *elapsed_ms);
+
+/* (2) one process per GPU (torch.distributed / MPI launchers): rank 0 exports its frame with bh_shared_frame_create, the
+ *     others map it (bh_shared_frame_open) and bind it (bh_ray_pipeline_bind_frame).  Ordering needs no collective: the
+ *     shared allocation carries BH_SHARED_FLAGS 32-bit flags after the frame; a rank signals "my rows of frame k are
+ *     stored" by a stream-ordered store of k into its flag (after its ray kernel, so the pixels are visible first), and
+ *     rank 0 waits — stream-ordered, on the device — until the flags of all ranks reach k.  The same pair orders
+ *     "rank 0 has consumed frame k" back to the writers.  Waits give up after timeout_ms (the error is reported by
+ *     bh_ctx_check_async) instead of hanging the GPU. */
+#define BH_SHARED_FLAGS 64
+uint32_t *bh_shared_frame_flags(void *device_ptr, size_t nbytes);   /* device pointer of flag 0 (nbytes as given to create) */
+int  bh_stream_signal(bh_ctx *ctx, uint32_t *device_flag, uint32_t value, void *cuda_stream);
+int  bh_stream_wait(bh_ctx *ctx, const uint32_t *device_flags, uint32_t n_flags, uint32_t value, uint32_t timeout_ms,
+                    void *cuda_stream);
+int  bh_ctx_check_async(bh_ctx *ctx);        /* BH_ERR_TIMEOUT if a bh_stream_wait on this context has given up since the last call */
+
+/* (3) end to end on N GPUs: a page-locked host frame in POSIX shared memory that every rank maps and registers with CUDA,
+ *     so each rank's kernel stores its own bands into the caller's frame over its own PCIe link (no NVLink hop, no D2H
+ *     copy).  The segment carries BH_SHARED_FLAGS host-side flags behind the frame for the processes to order themselves. */
+typedef struct bh_host_frame bh_host_frame;
+int   bh_host_frame_create(bh_ctx *ctx, const char *shm_name, size_t nbytes, int create, bh_host_frame **out);
+void  bh_host_frame_destroy(bh_host_frame *hf, int unlink_name);
+float *bh_host_frame_ptr(const bh_host_frame *hf);
+int   bh_host_frame_signal(bh_host_frame *hf, uint32_t slot, uint32_t value);
+int   bh_host_frame_wait(bh_host_frame *hf, uint32_t first_slot, uint32_t n_slots, uint32_t value, uint32_t timeout_ms);
+/* A (tiled) pipeline's pass with its rows stored at their GLOBAL row index into a full width x height page-locked host frame
+ * (bh_host_frame_ptr, or any cudaHostRegister'ed / cudaHostAlloc'ed mapped memory).  Asynchronous on `cuda_stream`. */
+int   bh_ray_pipeline_pass_to_host_frame(bh_ray_pipeline *p, const bh_camera_uniform *camera,
+                                         const bh_black_hole_uniform *black_hole, const bh_ray_details *details,
+                                         float *mapped_host_frame_rgba32f, void *cuda_stream);
 
 /* ---- post chain: the passes that consume the sky pass's output.  One object per pass, the same
  *      new / pass / output_view triple as the reference's BloomPipeline (bloom_pipline.rs:20,156,160; shaders
@@ -239,6 +310,11 @@ typedef struct bh_model_info {
     int32_t nodes_used, max_depth, leaf_count, max_leaf_size;
 } bh_model_info;
 int  bh_model_load_obj(const char *path, void *model_uniform, bh_model_info *info);
+/* Checks every index trace_ray_model (ray.wgsl:287-363) would follow from the root of a ModelUniform blob: children inside
+ * the node array and numbered after their parent, leaf ranges, lookup entries, point / normal indices.  The reference's
+ * WGSL clamps out-of-range indices (naga's Restrict policy); this library refuses such a blob: bh_ctx_upload_models calls
+ * this, bh_ctx_upload_models_async (the per-frame re-send) trusts its caller. */
+int  bh_model_validate(const void *model_uniform);
 /* points/normals: n*3 floats already in model space; tris: m*6 int32 (p1,p2,p3,n1,n2,n3) */
 int  bh_model_from_arrays(const float *points, int32_t n_points, const float *normals, int32_t n_normals,
                           const int32_t *tris, int32_t n_tris, const float position[3], int32_t visible,

@@ -35,6 +35,27 @@
 #include <omp.h>
 #endif
 
+/* Storage type of everything that crosses the oracle's API or lives in a reference byte layout: always binary32. */
+typedef float f32;
+
+#ifdef BHO_SHADOW
+/* float64 SHADOW flavour (SURVEY.md §8c parity protocol): the SAME source with every arithmetic `float` widened to
+ * binary64 and libm's double functions — inputs, constants and stored outputs stay binary32 (f32), so the only thing
+ * that changes is the rounding of the intermediate operations.  A pixel whose shadow result differs from the strict
+ * flavour's by more than the parity tolerance is ILL-CONDITIONED: its value is decided by f32 rounding (a ray grazing the
+ * photon sphere, a disk / mesh / horizon edge, a star edge in the sky map), and no two conforming WGSL implementations
+ * need agree on it.  tests/ and bench.py use it to classify the outliers of the device-vs-strict comparison.
+ * The BVH builder and OBJ loader below are written on f32 and are unaffected. */
+#define float double
+#define sqrtf sqrt
+#define floorf floor
+#define fabsf fabs
+#define truncf trunc
+#define fminf fmin
+#define fmaxf fmax
+#define fmaf fma
+#endif
+
 /* ------------------------------------------------------------------ byte layouts */
 #define MAX_MODEL_VERTICES 524288          /* triangle.rs:7, ray.wgsl:1 */
 #define MU_SIZE        48234572ULL         /* sizeof(ModelUniform), triangle.rs:268-285 */
@@ -49,8 +70,8 @@
 typedef struct { float x, y, z; } v3;
 
 typedef struct {                            /* ray.wgsl:85-90 / triangle.rs:45-52 */
-    float min_corner[3]; int32_t left_child;
-    float max_corner[3]; int32_t obj_count;
+    f32 min_corner[3]; int32_t left_child;
+    f32 max_corner[3]; int32_t obj_count;
 } bho_node;
 
 typedef struct { int32_t p1, p2, p3, n1, n2, n3; } bho_tri;   /* triangle.rs:54-63 */
@@ -159,7 +180,7 @@ static inline v3 mat3_mul(v3 c0, v3 c1, v3 c2, v3 v)   /* M*v = c0*v.x + c1*v.y 
 }
 
 /* ------------------------------------------------------------------ uniforms from raw bytes */
-static float rd_f32(const uint8_t *p) { float f; memcpy(&f, p, 4); return f; }
+static float rd_f32(const uint8_t *p) { f32 f; memcpy(&f, p, 4); return f; }
 static int32_t rd_i32(const uint8_t *p) { int32_t i; memcpy(&i, p, 4); return i; }
 static v3 rd_v3(const uint8_t *p) { return V(rd_f32(p), rd_f32(p + 4), rd_f32(p + 8)); }
 
@@ -246,21 +267,21 @@ static const float PI_F = 3.1415926f;   /* ray.wgsl:131, sky.wgsl:6 (Q19) */
 /* Cash–Karp tableau, ray.wgsl:133-165.  The WGSL `const a_21 = 1.0/5.0;` declarations are
  * AbstractFloat const-expressions (binary64) converted to f32 where they meet an f32 operand;
  * CHOICE: follow that rule, including the (b_i - b_a_i) differences at ray.wgsl:435. */
-#define A21 ((float)(1.0 / 5.0))
-#define A31 ((float)(3.0 / 40.0))
-#define A32 ((float)(9.0 / 40.0))
-#define A41 ((float)(3.0 / 10.0))
-#define A42 ((float)(-9.0 / 10.0))
-#define A43 ((float)(6.0 / 5.0))
-#define A51 ((float)(-11.0 / 54.0))
-#define A52 ((float)(5.0 / 2.0))
-#define A53 ((float)(-70.0 / 27.0))
-#define A54 ((float)(35.0 / 27.0))
-#define A61 ((float)(1631.0 / 55296.0))
-#define A62 ((float)(175.0 / 512.0))
-#define A63 ((float)(575.0 / 13824.0))
-#define A64 ((float)(44275.0 / 110592.0))
-#define A65 ((float)(253.0 / 4096.0))
+#define A21 ((f32)(1.0 / 5.0))
+#define A31 ((f32)(3.0 / 40.0))
+#define A32 ((f32)(9.0 / 40.0))
+#define A41 ((f32)(3.0 / 10.0))
+#define A42 ((f32)(-9.0 / 10.0))
+#define A43 ((f32)(6.0 / 5.0))
+#define A51 ((f32)(-11.0 / 54.0))
+#define A52 ((f32)(5.0 / 2.0))
+#define A53 ((f32)(-70.0 / 27.0))
+#define A54 ((f32)(35.0 / 27.0))
+#define A61 ((f32)(1631.0 / 55296.0))
+#define A62 ((f32)(175.0 / 512.0))
+#define A63 ((f32)(575.0 / 13824.0))
+#define A64 ((f32)(44275.0 / 110592.0))
+#define A65 ((f32)(253.0 / 4096.0))
 #define B1  (37.0 / 378.0)
 #define B2  (0.0)
 #define B3  (250.0 / 621.0)
@@ -434,8 +455,8 @@ static render_state trace_ray_model(const ctx_t *cx, ray_t ray, int model_index,
     const uint8_t *mu = cx->scene->models + (size_t)model_index * MU_SIZE;
     const bho_node *nodes = (const bho_node *)(mu + MU_NODES);
     const bho_tri *tris = (const bho_tri *)(mu + MU_TRIANGLES);
-    const float *points = (const float *)(mu + MU_POINTS);
-    const float *normals = (const float *)(mu + MU_NORMALS);
+    const f32 *points = (const f32 *)(mu + MU_POINTS);
+    const f32 *normals = (const f32 *)(mu + MU_NORMALS);
     const int32_t *lookup = (const int32_t *)(mu + MU_LOOKUP);
     v3 mpos = rd_v3(mu + MU_POSITION);
 
@@ -551,23 +572,23 @@ static rk_state_t next_ray_rk(const ctx_t *cx, rk_state_t st, tls_t *tls)
     v3 k_5 = accel(cx, vmadd(vmadd(k_4, A54, vmadd(k_3, A53, vmadd(k_2, A52, sscale(A51, k_1)))), h, ray.position), h2, r5);
     v3 k_6 = accel(cx, vmadd(vmadd(k_5, A65, vmadd(k_4, A64, vmadd(k_3, A63, vmadd(k_2, A62, sscale(A61, k_1))))), h, ray.position), h2, r5);
 
-    v3 esum = sscale((float)(B1 - BA1), k_1);
-    esum = vmadd(k_2, (float)(B2 - BA2), esum);
-    esum = vmadd(k_3, (float)(B3 - BA3), esum);
-    esum = vmadd(k_4, (float)(B4 - BA4), esum);
-    esum = vmadd(k_5, (float)(B5 - BA5), esum);
-    esum = vmadd(k_6, (float)(B6 - BA6), esum);
+    v3 esum = sscale((f32)(B1 - BA1), k_1);
+    esum = vmadd(k_2, (f32)(B2 - BA2), esum);
+    esum = vmadd(k_3, (f32)(B3 - BA3), esum);
+    esum = vmadd(k_4, (f32)(B4 - BA4), esum);
+    esum = vmadd(k_5, (f32)(B5 - BA5), esum);
+    esum = vmadd(k_6, (f32)(B6 - BA6), esum);
     v3 e = sscale(h, esum);
     /* yscal = 1, eps = 1: x/1 == x */
     st.e_max = bho_max(bho_max(fabsf(e.x), fabsf(e.y)), fabsf(e.z));
     if (!(st.e_max <= 1.0f)) tls->c.rk_reject++;
 
-    v3 dsum = sscale((float)BA1, k_1);
-    dsum = vmadd(k_2, (float)BA2, dsum);
-    dsum = vmadd(k_3, (float)BA3, dsum);
-    dsum = vmadd(k_4, (float)BA4, dsum);
-    dsum = vmadd(k_5, (float)BA5, dsum);
-    dsum = vmadd(k_6, (float)BA6, dsum);
+    v3 dsum = sscale((f32)BA1, k_1);
+    dsum = vmadd(k_2, (f32)BA2, dsum);
+    dsum = vmadd(k_3, (f32)BA3, dsum);
+    dsum = vmadd(k_4, (f32)BA4, dsum);
+    dsum = vmadd(k_5, (f32)BA5, dsum);
+    dsum = vmadd(k_6, (f32)BA6, dsum);
     st.ray.direction = vnormalize(vmadd(dsum, st.h, st.ray.direction));
     st.ray.position = vmadd(ray.direction, st.h, st.ray.position);                 /* Q6: OLD direction */
 
@@ -705,6 +726,28 @@ static ray_t create_ray(const ctx_t *cx, int px, int py, int sw, int sh)
     return r;
 }
 
+#ifdef BHO_SHADOW
+/* Conditioning probe of the shadow flavour: rotate every camera ray by `g_shadow_perturb` radians (about y, and 0.618x
+ * that about x) before it is traced.  |shadow(delta) - shadow(0)| > tolerance for a delta of the size of the rounding
+ * error a binary32 integration accumulates (measured: median 2e-7, 99th percentile 8e-7 on the exit direction) marks a
+ * pixel whose value no binary32 implementation can be expected to reproduce to that tolerance. */
+static double g_shadow_perturb = 0.0;
+void bho_shadow_set_perturbation(double radians) { g_shadow_perturb = radians; }
+static ray_t perturb_ray(ray_t r)
+{
+    if (g_shadow_perturb != 0.0) {
+        const double a = g_shadow_perturb, b = 0.618 * g_shadow_perturb;
+        v3 d = r.direction;
+        d = V(d.x + a * d.z, d.y, d.z - a * d.x);
+        d = V(d.x, d.y + b * d.z, d.z - b * d.y);
+        r.direction = vnormalize(d);
+    }
+    return r;
+}
+#else
+#define perturb_ray(r) (r)
+#endif
+
 /* ------------------------------------------------------------------ ray.wgsl:263-267 angle_between */
 static inline float angle_between(v3 a, v3 b)
 {
@@ -714,11 +757,11 @@ static inline float angle_between(v3 a, v3 b)
 }
 
 /* textureLoad on the previous level; CHOICE (Q18): out-of-range coordinates return a zero texel */
-static inline v4 prev_load(const float *prev, int pw, int ph, int x, int y)
+static inline v4 prev_load(const f32 *prev, int pw, int ph, int x, int y)
 {
     v4 z = { 0, 0, 0, 0 };
     if (x < 0 || y < 0 || x >= pw || y >= ph) return z;
-    const float *p = prev + 4 * ((size_t)y * (size_t)pw + (size_t)x);
+    const f32 *p = prev + 4 * ((size_t)y * (size_t)pw + (size_t)x);
     v4 r = { p[0], p[1], p[2], p[3] };
     return r;
 }
@@ -736,10 +779,10 @@ static void add_counters(bho_counters *a, const bho_counters *b)
  * prev == NULL (or 1x1) is the base case.  Aux outputs are nullable.
  * out_class: 0 traced(base) 1 copied 2 interpolated 3 traced(fine level). */
 int bho_ray_pass(const bho_scene *scene, int32_t w, int32_t h,
-                 const float *prev, int32_t pw, int32_t ph,
+                 const f32 *prev, int32_t pw, int32_t ph,
                  const uint8_t *camera32, const uint8_t *black_hole132, const uint8_t *details32,
                  int32_t row_begin, int32_t row_end,
-                 float *out_rgba, int32_t *out_hit, uint32_t *out_steps, uint8_t *out_class,
+                 f32 *out_rgba, int32_t *out_hit, uint32_t *out_steps, uint8_t *out_class,
                  bho_counters *counters, int32_t nthreads)
 {
     if (!scene || !camera32 || !black_hole132 || !details32 || !out_rgba) return -EINVAL;
@@ -769,7 +812,7 @@ int bho_ray_pass(const bho_scene *scene, int32_t w, int32_t h,
                 trace_out to; to.hit_tri = -1; to.steps = 0;
                 uint8_t cls;
                 if (base) {
-                    to = trace_ray(&cx, create_ray(&cx, x, y, w, h), &tls);
+                    to = trace_ray(&cx, perturb_ray(create_ray(&cx, x, y, w, h)), &tls);
                     cls = 0; tls.c.px_traced++;
                 } else {
                     int sfx = (w - 1) / (pw - 1), sfy = (h - 1) / (ph - 1);
@@ -799,7 +842,7 @@ int bho_ray_pass(const bho_scene *scene, int32_t w, int32_t h,
                             to.r = p.x; to.g = p.y; to.b = p.z; to.a = 0.0f;
                             cls = 2; tls.c.px_interp++;
                         } else {
-                            to = trace_ray(&cx, create_ray(&cx, x, y, w, h), &tls);
+                            to = trace_ray(&cx, perturb_ray(create_ray(&cx, x, y, w, h)), &tls);
                             cls = 3; tls.c.px_traced++;
                         }
                     }
@@ -819,7 +862,7 @@ int bho_ray_pass(const bho_scene *scene, int32_t w, int32_t h,
 }
 
 /* ------------------------------------------------------------------ float -> binary16, round to nearest even */
-static uint16_t f32_to_f16(float f)
+static uint16_t f32_to_f16(f32 f)
 {
     uint32_t x; memcpy(&x, &f, 4);
     uint32_t sign = (x >> 16) & 0x8000u;
@@ -843,9 +886,9 @@ static uint16_t f32_to_f16(float f)
 /* ------------------------------------------------------------------ sky.wgsl:8-30 main
  * One call = one SkyPipeline::pass (sky_pipeline.rs:140-148).  out_f32 (RGBA32F, before the
  * f16 store) and out_f16 (the reference's Rgba16Float, sky_pipeline.rs:34) are each nullable. */
-int bho_sky_pass(const bho_scene *scene, int32_t w, int32_t h, const float *prev,
+int bho_sky_pass(const bho_scene *scene, int32_t w, int32_t h, const f32 *prev,
                  int32_t row_begin, int32_t row_end,
-                 float *out_f32, uint16_t *out_f16, bho_counters *counters, int32_t nthreads)
+                 f32 *out_f32, uint16_t *out_f16, bho_counters *counters, int32_t nthreads)
 {
     if (!scene || !prev || w < 1 || h < 1 || row_begin < 0 || row_end > h || row_begin > row_end) return -EINVAL;
     bho_counters total; memset(&total, 0, sizeof total);
@@ -861,7 +904,7 @@ int bho_sky_pass(const bho_scene *scene, int32_t w, int32_t h, const float *prev
         for (int32_t y = row_begin; y < row_end; y++) {
             for (int32_t x = 0; x < w; x++) {
                 size_t o = (size_t)y * (size_t)w + (size_t)x;
-                const float *p = prev + 4 * o;
+                const f32 *p = prev + 4 * o;
                 float r, g, b, a;
                 if (p[3] == 0.0f) {
                     float u, v;
@@ -873,8 +916,8 @@ int bho_sky_pass(const bho_scene *scene, int32_t w, int32_t h, const float *prev
                 }
                 if (out_f32) { out_f32[4 * o] = r; out_f32[4 * o + 1] = g; out_f32[4 * o + 2] = b; out_f32[4 * o + 3] = a; }
                 if (out_f16) {
-                    out_f16[4 * o] = f32_to_f16(r); out_f16[4 * o + 1] = f32_to_f16(g);
-                    out_f16[4 * o + 2] = f32_to_f16(b); out_f16[4 * o + 3] = f32_to_f16(a);
+                    out_f16[4 * o] = f32_to_f16((f32)r); out_f16[4 * o + 1] = f32_to_f16((f32)g);
+                    out_f16[4 * o + 2] = f32_to_f16((f32)b); out_f16[4 * o + 3] = f32_to_f16((f32)a);
                 }
             }
         }
@@ -889,19 +932,19 @@ int bho_sky_pass(const bho_scene *scene, int32_t w, int32_t h, const float *prev
  * Operates in place on a verbatim ModelUniform blob whose points/triangles are already filled.
  * Literal recursion: children allocated as a consecutive pair, left subtree fully built first. */
 typedef struct {
-    float *points; bho_tri *tris; bho_node *nodes; int32_t *lookup; size_t nodes_used; int max_depth;
+    f32 *points; bho_tri *tris; bho_node *nodes; int32_t *lookup; size_t nodes_used; int max_depth;
 } bvh_build_t;
 
 static void bvh_update_bounds(bvh_build_t *b, size_t ni)       /* triangle.rs:159-194 */
 {
     bho_node *node = &b->nodes[ni];
-    const float fmax = 3.40282347e+38f;                          /* f32::MAX / f32::MIN */
-    for (int a = 0; a < 3; a++) { node->min_corner[a] = fmax; node->max_corner[a] = -fmax; }
+    const f32 flt_max = 3.40282347e+38f;                         /* f32::MAX / f32::MIN */
+    for (int a = 0; a < 3; a++) { node->min_corner[a] = flt_max; node->max_corner[a] = -flt_max; }
     for (int32_t i = 0; i < node->obj_count; i++) {
         const bho_tri *t = &b->tris[b->lookup[node->left_child + i]];
         const int32_t idx[3] = { t->p1, t->p2, t->p3 };
         for (int k = 0; k < 3; k++) {
-            const float *p = b->points + 4 * (size_t)idx[k];
+            const f32 *p = b->points + 4 * (size_t)idx[k];
             for (int a = 0; a < 3; a++) {
                 /* Rust f32::min/max: NaN-ignoring, same as fminf/fmaxf */
                 node->min_corner[a] = fminf(node->min_corner[a], p[a]);
@@ -915,18 +958,18 @@ static void bvh_subdivide(bvh_build_t *b, size_t ni, int depth)   /* triangle.rs
 {
     if (depth > b->max_depth) b->max_depth = depth;
     if (b->nodes[ni].obj_count <= 2) return;
-    float extent[3];
+    f32 extent[3];
     for (int a = 0; a < 3; a++) extent[a] = b->nodes[ni].max_corner[a] - b->nodes[ni].min_corner[a];
     int axis = 0;
     if (extent[1] > extent[axis]) axis = 1;
     if (extent[2] > extent[axis]) axis = 2;
-    float split_position = b->nodes[ni].min_corner[axis] + extent[axis] / 2.0f;
+    f32 split_position = b->nodes[ni].min_corner[axis] + extent[axis] / 2.0f;
 
     int32_t i = b->nodes[ni].left_child;
     int32_t j = i + b->nodes[ni].obj_count - 1;
     while (i <= j) {
         const bho_tri *t = &b->tris[b->lookup[i]];
-        float c = (b->points[4 * (size_t)t->p1 + axis] + b->points[4 * (size_t)t->p2 + axis] + b->points[4 * (size_t)t->p3 + axis]) / 3.0f;
+        f32 c = (b->points[4 * (size_t)t->p1 + axis] + b->points[4 * (size_t)t->p2 + axis] + b->points[4 * (size_t)t->p3 + axis]) / 3.0f;
         if (c < split_position) {
             i += 1;
         } else {
@@ -956,7 +999,7 @@ int64_t bho_build_bvh(uint8_t *model_uniform, int32_t triangle_count, int32_t *m
 {
     if (!model_uniform || triangle_count < 0 || triangle_count > MAX_MODEL_VERTICES) return -EINVAL;
     bvh_build_t b;
-    b.points = (float *)(model_uniform + MU_POINTS);
+    b.points = (f32 *)(model_uniform + MU_POINTS);
     b.tris = (bho_tri *)(model_uniform + MU_TRIANGLES);
     b.nodes = (bho_node *)(model_uniform + MU_NODES);
     b.lookup = (int32_t *)(model_uniform + MU_LOOKUP);
@@ -1012,14 +1055,14 @@ int64_t bho_load_obj(const char *path, uint8_t *model_uniform, int32_t *point_co
         while (*p && *p != '\n') p++;
         if (*p) p++;
     }
-    float *pos = (float *)malloc((nv + 1) * 3 * sizeof(float));
-    float *nrm = (float *)malloc((nvn + 1) * 3 * sizeof(float));
+    f32 *pos = (f32 *)malloc((nv + 1) * 3 * sizeof(f32));
+    f32 *nrm = (f32 *)malloc((nvn + 1) * 3 * sizeof(f32));
     imap_t vmap, nmap;
     if (!pos || !nrm || imap_init(&vmap, nv + 1) || imap_init(&nmap, nvn + 1)) { free(text); return -ENOMEM; }
 
     memset(model_uniform, 0, MU_SIZE);
-    float *points = (float *)(model_uniform + MU_POINTS);
-    float *normals = (float *)(model_uniform + MU_NORMALS);
+    f32 *points = (f32 *)(model_uniform + MU_POINTS);
+    f32 *normals = (f32 *)(model_uniform + MU_NORMALS);
     bho_tri *tris = (bho_tri *)(model_uniform + MU_TRIANGLES);
     int32_t point_count = 0, normal_count = 0, triangle_count = 0;
     int64_t rc = 0;
@@ -1094,13 +1137,14 @@ int64_t bho_load_obj(const char *path, uint8_t *model_uniform, int32_t *point_co
             if (!has_n) {
                 /* model.rs:56-68: face normal from the already-scaled points; index = running normal_count.
                  * NOTE: the lookup uses the un-offset index p (model.points[p1]) exactly like the reference. */
-                v3 a = V(points[4 * (size_t)pi[0]], points[4 * (size_t)pi[0] + 1], points[4 * (size_t)pi[0] + 2]);
-                v3 b2 = V(points[4 * (size_t)pi[1]], points[4 * (size_t)pi[1] + 1], points[4 * (size_t)pi[1] + 2]);
-                v3 c2 = V(points[4 * (size_t)pi[2]], points[4 * (size_t)pi[2] + 1], points[4 * (size_t)pi[2] + 2]);
-                v3 cr = vcross(vsub(b2, a), vsub(c2, a));
+                const f32 *a = points + 4 * (size_t)pi[0], *b2 = points + 4 * (size_t)pi[1], *c2 = points + 4 * (size_t)pi[2];
+                const f32 e1[3] = { b2[0] - a[0], b2[1] - a[1], b2[2] - a[2] }, e2[3] = { c2[0] - a[0], c2[1] - a[1], c2[2] - a[2] };
+                /* cgmath 0.18 Vector3::cross: (y*oz - z*oy, z*ox - x*oz, x*oy - y*ox), plain f32 ops (Rust never contracts) */
+                const f32 cr[3] = { e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0] };
                 /* cgmath 0.18 InnerSpace::normalize == self * (1 / magnitude) (recalled from the crate source,
                  * which is not vendored; only reached for OBJ files without `vn`, which lucy.obj is not) */
-                v3 dir = vscale(cr, 1.0f / vlength(cr));
+                const f32 inv = 1.0f / (f32)sqrt((double)(cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]));
+                const struct { f32 x, y, z; } dir = { cr[0] * inv, cr[1] * inv, cr[2] * inv };
                 if (normal_count >= MAX_MODEL_VERTICES) { rc = -E2BIG; break; }
                 int32_t index = normal_count;
                 normals[4 * (size_t)normal_count + 0] = dir.x; normals[4 * (size_t)normal_count + 1] = dir.y;
@@ -1117,7 +1161,7 @@ int64_t bho_load_obj(const char *path, uint8_t *model_uniform, int32_t *point_co
     if (rc) return rc;
 
     /* header: Model::new defaults (triangle.rs:100,108) via ModelUniform::update (triangle.rs:309-324) */
-    float hdr_pos[3] = { -10.0f, 0.0f, 30.0f };
+    f32 hdr_pos[3] = { -10.0f, 0.0f, 30.0f };
     memcpy(model_uniform + MU_POSITION, hdr_pos, 12);
     int32_t one = 1; memcpy(model_uniform + MU_VISIBLE, &one, 4);
     memcpy(model_uniform + 32, &point_count, 4);            /* point_count */
@@ -1132,6 +1176,7 @@ int64_t bho_load_obj(const char *path, uint8_t *model_uniform, int32_t *point_co
     return triangle_count;
 }
 
+#ifndef BHO_SHADOW                /* the post chain, the disk generator and the leaf-function KAT entry points exist in the f32 flavours only */
 #include "bh_oracle_post.inc"   /* post chain: bloom, mix, ACES, FXAA */
 
 /* ------------------------------------------------------------------ leaf-function entry points for KATs */
@@ -1253,8 +1298,12 @@ void bho_kat_math_array(int fn, const float *a, const float *b, float *out, int6
         }
     }
 }
+#endif /* !BHO_SHADOW */
 int bho_flavour(void)
 {
+#if defined(BHO_SHADOW)
+    return 3;
+#endif
 #if defined(BHO_FLAVOUR_CONTRACT) && defined(BHO_FUSED)
     return 2;
 #elif defined(BHO_FLAVOUR_CONTRACT)

@@ -7,6 +7,9 @@
  *
  *   BHO_FLAVOUR_STRICT   (default)  glibc libm float functions.  Neutral, independent of the
  *                                   product.  Also the CPU baseline that bench.py times.
+ *   BHO_SHADOW                      float64 SHADOW: binary64 glibc functions; bh_oracle.c widens every arithmetic
+ *                                   `float` to double with it (inputs, constants and outputs stay binary32).  Marks
+ *                                   the pixels whose value is decided by f32 rounding (ill-conditioned).
  *   BHO_FLAVOUR_CONTRACT            "det-math": every transcendental is evaluated in IEEE
  *                                   binary64 with explicit fma() and a fixed polynomial, then
  *                                   rounded once to binary32.  Uses only operations that are
@@ -172,7 +175,23 @@ static inline double bho_dm_pow(double x, double y)
 
 /* ---------------------------------------------------------------- flavour dispatch (binary32 API) */
 
-#if defined(BHO_FLAVOUR_CONTRACT)
+#if defined(BHO_SHADOW)
+
+/* float64 shadow flavour (bh_oracle.c): glibc's binary64 functions on binary64 operands */
+static inline double bho_sin(double x)  { return sin(x); }
+static inline double bho_cos(double x)  { return cos(x); }
+static inline double bho_tan(double x)  { return tan(x); }
+static inline double bho_atan2(double y, double x) { return atan2(y, x); }
+static inline double bho_acos(double x) { return acos(x); }
+static inline double bho_pow(double x, double y) { return pow(x, y); }
+static inline double bho_pow2(double x) { return pow(x, 2.0); }
+static inline double bho_pow4(double x) { return pow(x, 4.0); }
+static inline double bho_pow5(double x) { return pow(x, 5.0); }
+static inline double bho_min(double a, double b) { return fmin(a, b); }
+static inline double bho_max(double a, double b) { return fmax(a, b); }
+static inline double bho_clamp(double x, double lo, double hi) { return fmin(fmax(x, lo), hi); }
+
+#elif defined(BHO_FLAVOUR_CONTRACT)
 
 static inline float bho_sin(float x)  { double s, c; bho_dm_sincos((double)x, &s, &c); return (float)s; }
 static inline float bho_cos(float x)  { double s, c; bho_dm_sincos((double)x, &s, &c); return (float)c; }
@@ -206,8 +225,10 @@ static inline float bho_pow5(float x) { return powf(x, 5.0f); }
 #endif
 
 /* min/max/clamp: NaN-ignoring (C fminf/fmaxf == PTX min.f32/max.f32), DESIGN.md §4 */
+#if !defined(BHO_SHADOW)
 static inline float bho_min(float a, float b) { return fminf(a, b); }
 static inline float bho_max(float a, float b) { return fmaxf(a, b); }
 static inline float bho_clamp(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+#endif
 
 #endif /* BHO_MATH_H */

@@ -8,6 +8,9 @@ Flavours (see bho_math.h and the madd/vdivs helpers in bh_oracle.c):
   "contract"  det-math transcendentals, same literal op order -> bit-comparable with the kernel's LITERAL mode
   "fused"     det-math + explicit fma contraction + reciprocal-multiply for vec/scalar division
               -> bit-comparable with the kernel's FUSED mode (the fast default)
+  "shadow"    float64 shadow of "strict": the same source with every arithmetic float widened to double (f32 inputs,
+              constants and outputs).  |strict - shadow| > tolerance marks a pixel as ILL-CONDITIONED — decided by f32
+              rounding — which is how the outliers of a device-vs-strict comparison are classified.
 """
 from __future__ import annotations
 
@@ -39,7 +42,7 @@ class _Counters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in COUNTER_FIELDS]
 
 
-FLAVOURS = ("strict", "contract", "fused")
+FLAVOURS = ("strict", "contract", "fused", "shadow")
 
 
 def build(force: bool = False) -> None:
@@ -65,6 +68,11 @@ def _lib(flavour: str) -> C.CDLL:
         lib = C.CDLL(path)
         lib.bho_ray_pass.restype = C.c_int
         lib.bho_sky_pass.restype = C.c_int
+        lib.bho_max_threads.restype = C.c_int
+        if flavour == "shadow":                  # ray / sky pass only: no post chain, no leaf-function KAT entry points
+            assert lib.bho_flavour() == 3
+            _LIBS[flavour] = lib
+            return lib
         for n in ("bho_bloom_down", "bho_bloom_up", "bho_mix", "bho_hdr", "bho_fxaa"):
             getattr(lib, n).restype = C.c_int
         lib.bho_build_bvh.restype = C.c_int64
@@ -127,11 +135,19 @@ class RayResult:
     counters: dict
 
 
+SHADOW_PERTURBATION = 1e-6     # radians: about the rounding error a binary32 integration accumulates on a direction (99th pct 8e-7)
+
+
 def ray_pass(scene: OracleScene, w: int, h: int, camera: bytes, black_hole: bytes, details: bytes,
              prev: np.ndarray | None = None, rows: tuple[int, int] | None = None,
-             flavour: str = "strict", nthreads: int = 0, out: RayResult | None = None) -> RayResult:
-    """One RayPipeline::pass (ray_pipeline.rs:301-309) on the CPU."""
+             flavour: str = "strict", nthreads: int = 0, out: RayResult | None = None, perturb: float = 0.0) -> RayResult:
+    """One RayPipeline::pass (ray_pipeline.rs:301-309) on the CPU.  `perturb` (shadow flavour only): rotate every camera
+    ray by that many radians first — the conditioning probe."""
     lib = _lib(flavour)
+    if flavour == "shadow":
+        lib.bho_shadow_set_perturbation(C.c_double(perturb))
+    elif perturb:
+        raise ValueError("perturb is a probe of the shadow flavour")
     assert len(camera) == 32 and len(black_hole) == 132 and len(details) == 32
     if out is None:
         out = RayResult(np.zeros((h, w, 4), np.float32), np.full((h, w), -1, np.int32),
@@ -245,6 +261,39 @@ def disk_texture(w: int = 1000, h: int = 1000, flavour: str = "strict") -> np.nd
     if rc != 0:
         raise RuntimeError(f"bho_disk_texture failed: {rc}")
     return out
+
+
+def parity_report(dev_rgba: np.ndarray, strict_rgba: np.ndarray, shadow_rgba: np.ndarray | None = None, tol: float = 1e-4,
+                  shadow_perturbed_rgba: np.ndarray | None = None) -> dict:
+    """SURVEY §8c protocol: device output against the strict flavour — fraction of pixels with any channel beyond `tol`,
+    max abs difference, RMS — and, given the float64 shadow of the same frame, the share of those outliers that the
+    shadow marks ILL-CONDITIONED, plus the outlier fraction that remains on well-conditioned pixels.  A pixel is
+    ill-conditioned when (a) the strict binary32 evaluation itself is off the float64 one by more than `tol`, or (b) —
+    given `shadow_perturbed_rgba`, the shadow traced from camera rays rotated by SHADOW_PERTURBATION — a perturbation of
+    the size of binary32's accumulated rounding error moves the float64 result by more than `tol`."""
+    d = np.abs(dev_rgba.astype(np.float64) - strict_rgba.astype(np.float64))
+    d = np.where(np.isnan(d), np.inf, d)
+    same_nan = np.isnan(dev_rgba) & np.isnan(strict_rgba)
+    d = np.where(same_nan, 0.0, d)
+    bad = (d > tol).any(axis=-1)
+    fin = d[np.isfinite(d)]
+    rep = {"pixels": int(bad.size), "outliers": int(bad.sum()), "outlier_frac": float(bad.mean()),
+           "max_abs": float(fin.max()) if fin.size else 0.0, "rms": float(np.sqrt(np.mean(fin ** 2))) if fin.size else 0.0, "tol": tol}
+    if shadow_rgba is not None:
+        s = np.abs(strict_rgba.astype(np.float64) - shadow_rgba.astype(np.float64))
+        s = np.where(np.isnan(s), np.inf, s)
+        ill = (s > tol).any(axis=-1)
+        rep["criterion"] = "|strict - shadow| > tol"
+        if shadow_perturbed_rgba is not None:
+            q = np.abs(shadow_perturbed_rgba.astype(np.float64) - shadow_rgba.astype(np.float64))
+            q = np.where(np.isnan(q), np.inf, q)
+            ill = ill | (q > tol).any(axis=-1)
+            rep["criterion"] += f" or |shadow(rays rotated by {SHADOW_PERTURBATION:g} rad) - shadow| > tol"
+        rep["ill_conditioned_frac"] = float(ill.mean())
+        rep["outliers_ill_conditioned"] = int((bad & ill).sum())
+        rep["outliers_ill_conditioned_share"] = float((bad & ill).sum() / bad.sum()) if bad.sum() else 1.0
+        rep["outlier_frac_well_conditioned"] = float((bad & ~ill).sum() / bad.size)
+    return rep
 
 
 def new_model_blob() -> np.ndarray:

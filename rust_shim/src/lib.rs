@@ -106,3 +106,36 @@ pub fn build_pyramid(ctx: &CudaContext, base: (f32, f32), multiplier: f32, itera
     let sky = CudaSkyPipeline::new(ctx, levels.last().expect("at least one level"));
     (levels, sky)
 }
+
+/// The whole compute pass of `Renderer::render` (mod.rs:406-421) on N GPUs from this one thread: coarse pyramid levels
+/// replicated per device, the last level cut into cyclic row bands whose pixels every device stores straight into device 0's
+/// frame over NVLink, sky resolve on device 0 (`bh_frame_multi`, include/bh_abi.h).  Each context must already hold the
+/// textures and models.
+pub struct CudaFrameMulti { raw: *mut ffi::bh_frame_multi, pub resolution: (u32, u32) }
+
+impl CudaFrameMulti {
+    /// `base`, `multiplier`, `iterations` as in mod.rs:177-179 ((72, 41), 3, 4); `iterations == 1` renders `base` itself.
+    pub fn new(ctxs: &[&CudaContext], base: (u32, u32), multiplier: u32, iterations: u32, band_rows: u32) -> Self {
+        let raws: Vec<*mut ffi::bh_ctx> = ctxs.iter().map(|c| c.raw).collect();
+        let desc = ffi::bh_frame_multi_desc { base_width: base.0, base_height: base.1, levels: iterations, multiplier, band_rows,
+                                              sky_format: ffi::BH_SKY_RGBA16F };
+        let mut raw = ptr::null_mut();
+        check(unsafe { ffi::bh_frame_multi_create(raws.as_ptr(), raws.len() as u32, &desc, &mut raw) }, "bh_frame_multi_create");
+        let resolution = unsafe { (ffi::bh_frame_multi_width(raw), ffi::bh_frame_multi_height(raw)) };
+        Self { raw, resolution }
+    }
+    /// all ray levels + the sky resolve, enqueued on the object's own streams; returns at once like `ComputePass` recording
+    pub fn pass<C: bytemuck::Pod, B: bytemuck::Pod, D: bytemuck::Pod>(&mut self, camera: &C, black_hole: &B, details: &D) {
+        assert_eq!((std::mem::size_of::<C>(), std::mem::size_of::<B>(), std::mem::size_of::<D>()), (32, 132, 32));
+        check(unsafe { ffi::bh_frame_multi_pass(self.raw, bytemuck::bytes_of(camera).as_ptr() as *const c_void,
+                                                bytemuck::bytes_of(black_hole).as_ptr() as *const c_void,
+                                                bytemuck::bytes_of(details).as_ptr() as *const c_void) }, "bh_frame_multi_pass");
+    }
+    /// `SkyPipeline::output_view` of the assembled frame: device pointer (device 0), Rgba16Float
+    pub fn output_view(&self) -> *const c_void { unsafe { ffi::bh_frame_multi_sky_output(self.raw) } }
+    pub fn read(&mut self, host_rgba16f: &mut [u16]) {
+        assert_eq!(host_rgba16f.len(), self.resolution.0 as usize * self.resolution.1 as usize * 4);
+        check(unsafe { ffi::bh_frame_multi_read(self.raw, ptr::null_mut(), host_rgba16f.as_mut_ptr() as *mut c_void) }, "bh_frame_multi_read");
+    }
+}
+impl Drop for CudaFrameMulti { fn drop(&mut self) { unsafe { ffi::bh_frame_multi_destroy(self.raw) } } }

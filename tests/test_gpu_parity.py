@@ -21,8 +21,14 @@ pytestmark = pytest.mark.gpu
 
 AUX = P.AUX_HIT | P.AUX_STEPS | P.AUX_CLASS
 TOL = 1e-4                 # BASELINE.json north_star: 1e-4 per RGBA channel
-STRICT_OUTLIER_FRAC = 3e-3  # pixels allowed beyond TOL vs the libm flavour: discontinuities (disk/mesh/horizon edges, star edges)
-                            # flip under ANY rounding change; measured 6e-5 (literal) .. 1e-3 (fused) on the test frames
+# Pixels allowed beyond TOL against the neutral libm flavour, per numeric mode: 2x the worst value MEASURED on these test
+# frames (tools/parity_report.py and the per-test figures in profiles/r2_parity_report.json: LITERAL 3.5e-4 on the 384x216 mesh
+# frame seen from outside the sphere, FUSED 1.76e-3 on C1's Euler frame).  The float64 shadow shows where they sit: 95-100 % of them are pixels whose
+# value a 1e-6 rad rotation of the camera ray moves by more than TOL (photon-sphere grazers, disk / mesh / horizon edges,
+# star edges): tests/test_gpu_fullsize.py asserts that at BASELINE sizes.
+STRICT_OUTLIER_FRAC = {"contract": 7e-4, "fused": 3.6e-3}
+STRICT_MIN_HIT_EQUAL = 0.9999        # measured >= 0.99999
+STRICT_MIN_STEPS_EQUAL = 0.9994      # measured >= 0.9997
 
 
 MODES = [pytest.param(P.NUMERIC_LITERAL, id="literal"), pytest.param(P.NUMERIC_FUSED, id="fused")]
@@ -79,11 +85,11 @@ def assert_stats(st, counters):
     assert st["rk_reject"] == counters["rk_reject"] and st["stack_overflow"] == counters["stack_overflow"]
 
 
-def assert_close_to_strict(dev, strict, what=""):
+def assert_close_to_strict(dev, strict, flavour, what=""):
     d = np.abs(dev["rgba"].astype(np.float64) - strict.rgba.astype(np.float64))
     bad = (d > TOL).any(axis=2).mean()
-    assert bad <= STRICT_OUTLIER_FRAC, f"{what}: {bad:.4%} of pixels beyond {TOL} vs libm oracle (max {d.max():.3g})"
-    assert (dev["hit"] == strict.hit).mean() >= 0.999 and (dev["steps"] == strict.steps).mean() >= 0.998
+    assert bad <= STRICT_OUTLIER_FRAC[flavour], f"{what}: {bad:.4%} of pixels beyond {TOL} vs libm oracle (max {d.max():.3g})"
+    assert (dev["hit"] == strict.hit).mean() >= STRICT_MIN_HIT_EQUAL and (dev["steps"] == strict.steps).mean() >= STRICT_MIN_STEPS_EQUAL
 
 
 # ------------------------------------------------------------------ det-math: device == oracle contract flavour, bit for bit
@@ -120,7 +126,7 @@ def test_small_scene_bit_exact(ctx_small, oracle, small_oracle_scene, method, ca
     assert_bit_exact(dev, ora, f"method {method} cam {campos}")
     assert_stats(st, ora.counters)
     strict = oracle.ray_pass(small_oracle_scene, w, h, cam.uniform(), hole.uniform(), det.uniform(), flavour="strict")
-    assert_close_to_strict(dev, strict)
+    assert_close_to_strict(dev, strict, fl(ctx_small))
     rp.close()
 
 
@@ -294,7 +300,7 @@ def test_c1_config(real_scene, oracle):
     ora = oracle.ray_pass(osc, 256, 256, cam.uniform(), hole.uniform(), det.uniform(), flavour=fl(ctx))
     assert_bit_exact(dev, ora, "C1")
     assert_stats(st, ora.counters)
-    assert_close_to_strict(dev, oracle.ray_pass(osc, 256, 256, cam.uniform(), hole.uniform(), det.uniform(), flavour="strict"), "C1")
+    assert_close_to_strict(dev, oracle.ray_pass(osc, 256, 256, cam.uniform(), hole.uniform(), det.uniform(), flavour="strict"), fl(ctx), "C1")
     rp.close()
 
 
@@ -311,7 +317,7 @@ def test_mesh_scene_hit_indices(real_scene, oracle, campos, fwd):
     assert (dev["hit"] >= 0).sum() > 500
     assert st["stack_overflow"] == 0          # Q16: the 19-entry stack never overflows in the test configs
     strict = oracle.ray_pass(osc, w, h, cam.uniform(), hole.uniform(), det.uniform(), flavour="strict")
-    assert_close_to_strict(dev, strict, f"mesh cam {campos}")
+    assert_close_to_strict(dev, strict, fl(ctx), f"mesh cam {campos}")
     rp.close()
 
 
@@ -457,9 +463,9 @@ def test_error_codes(small_scene):
 # ------------------------------------------------------------------ BASELINE.json full sizes: properties + oracle spot checks
 @pytest.mark.parametrize("w,h,mc", [(1920, 1080, 0), (3840, 2160, 1)])
 def test_full_size_properties(real_scene, oracle, w, h, mc):
-    """C2 (1920x1080 RK, disk) and C3 (3840x2160 RK, disk + sphere + 100k-tri BVH): the oracle is too slow
-    for whole frames here, so check (a) oracle parity on sampled rows, (b) determinism, (c) step-count
-    bookkeeping, (d) output invariants."""
+    """C2 (1920x1080 RK, disk) and C3 (3840x2160 RK, disk + sphere + 100k-tri BVH): size-independent properties —
+    (a) oracle parity on sampled rows, (b) determinism, (c) step-count bookkeeping, (d) output invariants.
+    (Every pixel of these frames is compared with the oracle in tests/test_gpu_fullsize.py.)"""
     ctx, osc, src = real_scene
     cam, hole, det = U.Camera(), U.BlackHole(), U.RayDetails(integration_method=1, model_count=mc)
     rp, dev, st = render(ctx, w, h, cam, hole, det, aux=P.AUX_HIT | P.AUX_STEPS)

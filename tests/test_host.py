@@ -50,7 +50,7 @@ def test_abi_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.bh_abi_version() == 1
+    assert lib.bh_abi_version() == _lib.ABI_VERSION == 2
     # struct sizes the ABI promises
     assert C.sizeof(_lib.PassStats) == 72 and C.sizeof(_lib.ModelInfo) == 28
 
