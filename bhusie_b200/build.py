@@ -1,6 +1,6 @@
 """Builds libbhray.so (the C-ABI library: CUDA kernels + host code) in-tree with nvcc for sm_100a.
 
-    python -m bhusie_b200.build [--force] [--verbose] [--pair]
+    python -m bhusie_b200.build [--force] [--verbose] [--hash]
 
 Flags that matter for parity: --fmad=false (no implicit FMA contraction),
 IEEE division and square root (nvcc defaults -prec-div=true -prec-sqrt=true; no -use_fast_math).
@@ -17,7 +17,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libbhray.so")
 SOURCES = ["bh_abi.cu", "bh_multi.cu", "ray_kernels.cu", "model_host.cpp"]
-HEADERS = ["bh_device.h", "bh_objects.h", "detmath.cuh", "ray_impl.cuh", "ray_pair.cuh", "post_impl.cuh", os.path.join("..", "..", "include", "bh_abi.h")]
+HEADERS = ["bh_device.h", "bh_objects.h", "detmath.cuh", "ray_impl.cuh", "post_impl.cuh", os.path.join("..", "..", "include", "bh_abi.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -43,7 +43,7 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-KERNEL_SOURCES = ["ray_impl.cuh", "ray_kernels.cu", "detmath.cuh", "bh_device.h", "ray_pair.cuh"]
+KERNEL_SOURCES = ["ray_impl.cuh", "ray_kernels.cu", "detmath.cuh", "bh_device.h"]
 
 
 def kernel_source_hash() -> str:
@@ -80,10 +80,5 @@ def build_library(force: bool = False, verbose: bool = False, extra: list[str] |
 if __name__ == "__main__":
     if "--hash" in sys.argv:
         print(kernel_source_hash())
-    elif "--pair" in sys.argv:
-        # the experimental two-rays-per-thread kernel (csrc/ray_pair.cuh) as a second library; run anything against it
-        # with BHRAY_LIB=bhusie_b200/lib/libbhray_pair.so (e.g. the whole `pytest -m gpu` suite: it is bit-identical)
-        print(build_library(force=True, verbose="--verbose" in sys.argv, extra=["-DBH_USE_PAIR=1"],
-                            out=os.path.join(LIB_DIR, "libbhray_pair.so")))
     else:
         print(build_library(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

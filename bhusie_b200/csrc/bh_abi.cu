@@ -308,11 +308,7 @@ int bh::build_pass_params(bh_ray_pipeline *p, const bh_camera_uniform *camera, c
     P.tile_rows = 4;
     P.item_begin = 0;
     P.n_items = (unsigned)P.tiles_x * (unsigned)((p->local_rows + 3) / 4);
-    {   // conservative bound used only to SKIP a test whose outcome is then provably "miss" (any value >= 1.001 |n| is valid)
-        const float *n = P.hole.normal;
-        const float nn = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
-        P.disk_k = (nn > 1e-30f && nn < 1e30f) ? 1.0021f * sqrtf(nn) : INFINITY;
-    }
+    derive_pass_constants(P);
     return BH_OK;
 }
 

@@ -1,6 +1,7 @@
 // bh_device.h — structures shared by the C-ABI host code (bh_abi.cu) and the kernels (ray_kernels.cu).
 #pragma once
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 #include "../../include/bh_abi.h"
 
@@ -54,7 +55,24 @@ struct PassParams {
     int tiles_x;
     unsigned int tile_rows;          // rows of a tile-mode work item: 4 (8x4 pixels, 32 rays per warp), or 2 / 1 on launches that do not fill the GPU
     float disk_k;                    // 1.0021 * |hole.normal| (+inf when degenerate): fast disk-plane rejection, ray_impl.cuh hot_iteration
+    float disk_far;                  // 1.001 * accretion_disk_outer (+inf when unusable): a segment that starts farther than
+                                     // disk_far + 1.01 h from the hole cannot reach the annulus, ray_impl.cuh hot_iteration
 };
+
+// The two constants above, derived once per pass on the host.  They only ever SKIP a test whose outcome is then provably
+// "miss", so any value at least as large as stated is valid; degenerate inputs disable the shortcut (+inf).
+inline void derive_pass_constants(PassParams &P)
+{
+    const float *n = P.hole.normal;
+    const float nn = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+    P.disk_k = (nn > 1e-30f && nn < 1e30f) ? 1.0021f * sqrtf(nn) : INFINITY;
+    // |ip - bh| >= |p - bh| - t |d| for every point of the segment; the 0.1 % margin covers the rounding of the computed
+    // distances as long as the hole is not placed absurdly far from the origin (absolute rounding error ~ 1e-7 |bh|)
+    const float outer = P.hole.accretion_disk_outer;
+    const float *b = P.hole.position;
+    const float bmax = fmaxf(fmaxf(fabsf(b[0]), fabsf(b[1])), fabsf(b[2]));
+    P.disk_far = (outer > 1e-3f && outer < 1e30f && bmax <= 64.0f * outer) ? 1.001f * outer : INFINITY;
+}
 
 struct SkyParams {
     DevTexture sky;

@@ -77,16 +77,6 @@ constexpr int kTopBytes = kTopHeaderBytes + kTopNodes * 32;
 #ifndef BH_SHADE_BATCH
 #define BH_SHADE_BATCH 8
 #endif
-#ifndef BH_OCC_PAIR
-#define BH_OCC_PAIR 4
-#endif
-// 1: FUSED mode runs the experimental two-rays-per-thread kernel (ray_pair.cuh: bit-identical, same speed); 0: one ray per thread
-#ifndef BH_USE_PAIR
-#define BH_USE_PAIR 0
-#endif
-#ifndef BH_PAIR_UNROLL
-#define BH_PAIR_UNROLL 0
-#endif
 
 #define BH_NUM_NS lit
 #define BH_FUSED 0
@@ -214,8 +204,7 @@ static cudaError_t launch_trace_mode(const PassParams &p, const LaunchConfig &cf
     const unsigned items = QUEUE ? (unsigned)(((size_t)p.local_rows * (size_t)p.w + 7) / 8) : p.n_items - p.item_begin;
     // Euler only: the higher-occupancy build when every warp of it would still get several items (tile mode knows the count)
     const bool hi = !QUEUE && euler && BH_OCC_EULER != 4 && items >= 6u * (unsigned)cfg.sm_count * 4u * (unsigned)BH_OCC_EULER;
-    // (the experimental two-rays-per-thread kernel keeps its 8x8 items)
-    if (!BH_USE_PAIR && !QUEUE && p.tile_rows == 4 && p.item_begin == 0 && p.n_items == (unsigned)p.tiles_x * (unsigned)((p.local_rows + 3) / 4)) {
+    if (!QUEUE && p.tile_rows == 4 && p.item_begin == 0 && p.n_items == (unsigned)p.tiles_x * (unsigned)((p.local_rows + 3) / 4)) {
         // whole-frame tile launch with fewer 8x4 tiles than warp slots: 8x2 or 8x1 tiles (see trace_kernel)
         const unsigned slots = (unsigned)cfg.sm_count * 4u * 4u;
         for (unsigned r = 1; r <= 2; r *= 2) {
@@ -238,16 +227,6 @@ static cudaError_t launch_trace_mode(const PassParams &p, const LaunchConfig &cf
     unsigned pos_bits[3];
     memcpy(pos_bits, p.hole.position, sizeof pos_bits);
     const bool origin = (pos_bits[0] | pos_bits[1] | pos_bits[2]) == 0u;
-#if BH_USE_PAIR
-    {   // two rays per thread: a warp item is an 8x8 tile (two tile rows) / 64 queue entries
-        const unsigned tile_rows = QUEUE ? 0u : (p.n_items - p.item_begin) / (unsigned)p.tiles_x;
-        const unsigned pair_items = QUEUE ? (items + 1u) / 2u : ((tile_rows + 1u) / 2u) * (unsigned)p.tiles_x;
-        if (origin) return euler ? launch_trace(fus::trace_pair_kernel<0, QUEUE, true>, pair_items, p, cfg, stream)
-                                 : launch_trace(fus::trace_pair_kernel<1, QUEUE, true>, pair_items, p, cfg, stream);
-        return euler ? launch_trace(fus::trace_pair_kernel<0, QUEUE, false>, pair_items, p, cfg, stream)
-                     : launch_trace(fus::trace_pair_kernel<1, QUEUE, false>, pair_items, p, cfg, stream);
-    }
-#else
     if (origin) {
         if (!euler) return launch_trace(fus::trace_kernel<1, QUEUE, BH_OCC_RK, true>, items, p, cfg, stream);
         if (!QUEUE && hi) return launch_trace(fus::trace_kernel<0, false, BH_OCC_EULER, true>, items, p, cfg, stream);
@@ -256,7 +235,6 @@ static cudaError_t launch_trace_mode(const PassParams &p, const LaunchConfig &cf
     if (!euler) return launch_trace(fus::trace_kernel<1, QUEUE, BH_OCC_RK, false>, items, p, cfg, stream);
     if (!QUEUE && hi) return launch_trace(fus::trace_kernel<0, false, BH_OCC_EULER, false>, items, p, cfg, stream);
     return launch_trace(fus::trace_kernel<0, QUEUE, 4, false>, items, p, cfg, stream);
-#endif
 }
 
 cudaError_t launch_ray_pass(const PassParams &p, const LaunchConfig &cfg, cudaStream_t stream)

@@ -69,9 +69,6 @@ static inline void mbar_wait(unsigned long long *, unsigned) {}
 constexpr int kTopNodes = 256;
 constexpr int kTopHeaderBytes = 64;
 constexpr int kTopBytes = kTopHeaderBytes + kTopNodes * 32;
-#ifndef BH_USE_PAIR
-#define BH_USE_PAIR 0          // -DBH_USE_PAIR=1: also the experimental two-rays-per-thread kernel (mode 2)
-#endif
 #define BH_SHADE_BATCH 8
 #define BH_NUM_NS lit
 #define BH_FUSED 0
@@ -108,11 +105,7 @@ extern "C" int bh_host_kernel_pass(int mode, const void *camera, const void *hol
     P.tiles_x = (w + 7) / 8; P.tile_rows = 4;
     unsigned long long stats[kStatCount] = { 0 };
     P.stats = stats;
-    {   // same expression as build_pass_params (bh_abi.cu)
-        const float *n = P.hole.normal;
-        const float nn = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
-        P.disk_k = (nn > 1e-30f && nn < 1e30f) ? 1.0021f * sqrtf(nn) : INFINITY;
-    }
+    derive_pass_constants(P);
     unsigned pos_bits[3];
     memcpy(pos_bits, P.hole.position, sizeof pos_bits);
     const bool origin = mode == 1 && (pos_bits[0] | pos_bits[1] | pos_bits[2]) == 0u;      // launch_trace_mode's choice
@@ -131,26 +124,6 @@ extern "C" int bh_host_kernel_pass(int mode, const void *camera, const void *hol
                 if (P.det.model_count > 0) { memcpy(fus::s_model_top, models, 48); memcpy(fus::s_model_top + kTopHeaderBytes, models + kMuNodes, kTopNodes * 32); }
             }
             float4 rgba; int tri; unsigned steps;
-#if BH_USE_PAIR
-            if (mode == 2) {
-                // two-rays-per-thread kernel (FUSED): this pixel and its right-hand neighbour as the thread's pair
-                if (x & 1) continue;
-                const bool second = x + 1 < w;
-                fus::LaneOut o0, o1;
-                if (origin2) { if (rk) fus::trace_warp_pair<1, true>(P, true, x, y, second, x + 1, y, o0, o1); else fus::trace_warp_pair<0, true>(P, true, x, y, second, x + 1, y, o0, o1); }
-                else         { if (rk) fus::trace_warp_pair<1, false>(P, true, x, y, second, x + 1, y, o0, o1); else fus::trace_warp_pair<0, false>(P, true, x, y, second, x + 1, y, o0, o1); }
-                for (int k = 0; k < kStatCount; ++k) stats[k] += fus::s_warp_stats[0][k];
-                for (int r = 0; r < (second ? 2 : 1); ++r) {
-                    const fus::LaneOut &o = r ? o1 : o0;
-                    const size_t idx = (size_t)y * (size_t)w + (size_t)(x + r);
-                    memcpy(out_rgba + 4 * idx, &o.rgba, 16);
-                    if (out_hit) out_hit[idx] = o.tri;
-                    if (out_steps) out_steps[idx] = o.steps;
-                    steps_total += o.steps; ++traced;
-                }
-                continue;
-            }
-#endif
             if (mode == 0) {
                 const lit::LaneOut o = rk ? lit::trace_warp<1, false>(P, true, x, y) : lit::trace_warp<0, false>(P, true, x, y);
                 rgba = o.rgba; tri = o.tri; steps = o.steps;

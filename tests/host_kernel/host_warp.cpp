@@ -101,7 +101,6 @@ static inline void mbar_wait(unsigned long long *, unsigned) {}
 constexpr int kTopNodes = 256;
 constexpr int kTopHeaderBytes = 64;
 constexpr int kTopBytes = kTopHeaderBytes + kTopNodes * 32;
-#define BH_USE_PAIR 0
 #define BH_SHADE_BATCH 8
 #define BH_NUM_NS lit
 #define BH_FUSED 0
@@ -164,11 +163,7 @@ extern "C" int bh_host_warp_level(int mode, const void *camera, const void *hole
     unsigned work[kWorkCount] = { 0 };
     std::vector<unsigned> queue((size_t)w * (size_t)local_rows + 1);
     P.stats = stats; P.work = work; P.queue = queue.data();
-    {   // same expression as build_pass_params (bh_abi.cu)
-        const float *n = P.hole.normal;
-        const float nn = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
-        P.disk_k = (nn > 1e-30f && nn < 1e30f) ? 1.0021f * sqrtf(nn) : INFINITY;
-    }
+    derive_pass_constants(P);
     unsigned pos_bits[3];
     memcpy(pos_bits, P.hole.position, sizeof pos_bits);
     const bool origin = mode == 1 && (pos_bits[0] | pos_bits[1] | pos_bits[2]) == 0u;

@@ -166,7 +166,7 @@ def test_c4_8k_as_eight_tiled_ranks(ctx, scene, oracle):
         rp.pass_(cam, hole, det)
         part, st = rp.read(), rp.stats()
         rows = lay.rows_of(rank)
-        assert part["rgba"].shape[0] == len(rows) == H // world
+        assert part["rgba"].shape[0] == len(rows) and abs(len(rows) - H // world) <= band
         assert st["ray_steps"] == int(part["steps"].sum(dtype=np.int64)) and st["px_traced"] == len(rows) * W
         total_steps += st["ray_steps"]
         # rows around the hole / disk / mesh (middle of the frame) and two random ones

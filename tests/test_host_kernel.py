@@ -20,9 +20,8 @@ from bhusie_b200 import uniforms as U
 
 SRC = os.path.join(ROOT, "tests", "host_kernel", "host_kernel.cpp")
 OUT = os.path.join(ROOT, "tests", "host_kernel", "_build", "libbh_host_kernel.so")
-OUT_PAIR = os.path.join(ROOT, "tests", "host_kernel", "_build", "libbh_host_kernel_pair.so")
-DEPS = [SRC] + [os.path.join(ROOT, "bhusie_b200", "csrc", f) for f in ("ray_impl.cuh", "ray_pair.cuh", "detmath.cuh", "bh_device.h")]
-FLAVOUR = {0: "contract", 1: "fused", 2: "fused"}         # mode 2: the experimental two-rays-per-thread kernel (FUSED)
+DEPS = [SRC] + [os.path.join(ROOT, "bhusie_b200", "csrc", f) for f in ("ray_impl.cuh", "detmath.cuh", "bh_device.h")]
+FLAVOUR = {0: "contract", 1: "fused"}
 STAT_NAMES = ("steps", "px_traced", "px_copied", "px_interp", "node_visits", "tri_tests", "tex_samples", "rk_reject", "stack_overflow")
 
 
@@ -45,11 +44,6 @@ def _build(out, extra):
 @pytest.fixture(scope="session")
 def host_kernel():
     return _build(OUT, [])
-
-
-@pytest.fixture(scope="session")
-def host_kernel_pair():
-    return _build(OUT_PAIR, ["-DBH_USE_PAIR=1"])
 
 
 def host_pass(lib, mode, tex, blob, w, h, cam, hole, det):
@@ -92,25 +86,6 @@ def test_device_source_on_cpu_matches_oracle(host_kernel, oracle, small_scene, s
     w, h = 33, 19                                     # odd: the centre pixel has zero angular momentum (sqrt operand exactly 0)
     rgba, hit, steps, st = host_pass(host_kernel, mode, tex, blob, w, h, cam, hole, det)
     ora = oracle.ray_pass(small_oracle_scene, w, h, cam.uniform(), hole.uniform(), det.uniform(), flavour=FLAVOUR[mode])
-    same = bits(rgba) == bits(ora.rgba)
-    assert same.all(), f"{case}: {(~same).mean():.3%} of RGBA words differ"
-    assert np.array_equal(hit, ora.hit) and np.array_equal(steps, ora.steps)
-    for k in ("steps", "px_traced", "node_visits", "tri_tests", "tex_samples", "rk_reject", "stack_overflow"):
-        assert st[k] == ora.counters[k], (k, st[k], ora.counters[k])
-
-
-@pytest.mark.parametrize("method", [0, 1], ids=["euler", "rk"])
-@pytest.mark.parametrize("case", list(CASES))
-def test_two_ray_kernel_source_on_cpu_matches_oracle(host_kernel_pair, oracle, small_scene, small_oracle_scene, method, case):
-    """The experimental two-rays-per-thread kernel (csrc/ray_pair.cuh, not in the product library): horizontally adjacent
-    pixels as a thread's pair; same oracle, same bits."""
-    tex, blob, _ = small_scene
-    ck, hk, dk = CASES[case]
-    cam, hole = U.Camera(**ck), U.BlackHole(**hk)
-    det = U.RayDetails(integration_method=method, model_count=1, time=1.25, **dk)
-    w, h = 33, 19                                     # odd width: the last pixel of a row is a pair with one ray
-    rgba, hit, steps, st = host_pass(host_kernel_pair, 2, tex, blob, w, h, cam, hole, det)
-    ora = oracle.ray_pass(small_oracle_scene, w, h, cam.uniform(), hole.uniform(), det.uniform(), flavour="fused")
     same = bits(rgba) == bits(ora.rgba)
     assert same.all(), f"{case}: {(~same).mean():.3%} of RGBA words differ"
     assert np.array_equal(hit, ora.hit) and np.array_equal(steps, ora.steps)
