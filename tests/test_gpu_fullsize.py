@@ -94,8 +94,11 @@ def check_frame(oracle, osc, ctx, name, dev, st, w, h, cam, hole, det, prev=None
         rep["step_count_equal_frac"] = float((dev["steps"] == strict.steps).mean())
         _REPORT[f"{name}/{mode}"] = rep
         _dump()
-        assert rep["outlier_frac"] <= MAX_OUTLIER_FRAC[mode], (name, rep)
-        assert rep["outlier_frac_well_conditioned"] <= MAX_WELL_CONDITIONED_OUTLIER_FRAC[mode], (name, rep)
+        # (small levels: a handful of pixels is a large fraction of 3 000, so the fractions apply from ~100 000 pixels up and
+        #  a fixed count below: 32 outliers, 8 of them on well-conditioned pixels)
+        n_px = rep["pixels"]
+        assert rep["outliers"] <= max(MAX_OUTLIER_FRAC[mode] * n_px, 32), (name, rep)
+        assert rep["outlier_frac_well_conditioned"] * n_px <= max(MAX_WELL_CONDITIONED_OUTLIER_FRAC[mode] * n_px, 8), (name, rep)
         assert rep["hit_index_equal_frac"] >= 0.9995, (name, rep)        # north star: hit indices bit-exact — they are, vs the mode's flavour;
         assert rep["step_count_equal_frac"] >= 0.999, (name, rep)        # vs libm a few edge pixels flip
     return ora

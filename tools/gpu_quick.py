@@ -46,6 +46,22 @@ def main():
     rp.close()
     ctx.set_numeric_mode(P.NUMERIC_FUSED)
     cam = U.Camera()
+    # one rank's share of a tiled frame, on one device: where does the 1 -> 8 GPU kernel-time overhead come from?
+    det = U.RayDetails(integration_method=1, model_count=1)
+    for world in (2, 4, 8, 16):
+        t = P.RayPipeline(ctx, 3840, 2160)
+        t.set_tiling(8, 1, world)
+        ms = timed(lambda: t.pass_(cam, hole, det, s), s, 2, 8)
+        st = t.stats()
+        out[f"tiled_rank1_of_{world}"] = {"ms": ms, "ms_ideal": out["c3_rk_fused"]["ms"] * st["ray_steps"] / out["c3_rk_fused"]["ray_steps"],
+                                          "ray_steps": st["ray_steps"], "local_rows": t.local_rows}
+        print(f"tiled 1 of {world}", out[f"tiled_rank1_of_{world}"], flush=True)
+        t.close()
+    small = P.RayPipeline(ctx, 3840, 272)          # the same pixel count as one rank of 8, as a plain frame of its own
+    ms = timed(lambda: small.pass_(cam, hole, det, s), s, 2, 8)
+    out["plain_3840x272"] = {"ms": ms, "ray_steps": small.stats()["ray_steps"], "gsteps_per_s": small.stats()["ray_steps"] / ms / 1e6}
+    print("plain 3840x272", out["plain_3840x272"], flush=True)
+    small.close()
     for name, base in (("pyramid_1918x1081", (72, 41)), ("pyramid_3835x2161", (143, 81))):
         for method, mname in ((0, "euler"), (1, "rk")):
             det = U.RayDetails(integration_method=method, model_count=1)
