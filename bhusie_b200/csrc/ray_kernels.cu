@@ -76,9 +76,6 @@ constexpr int kTopBytes = kTopHeaderBytes + kTopNodes * 32;
 // lanes of a warp that must wait for disk shading before the hot phase is interrupted for them (1 = serve every crossing at once)
 #ifndef BH_SHADE_BATCH
 #define BH_SHADE_BATCH 8
-#ifndef BH_SERVE_DIV
-#define BH_SERVE_DIV 4u        // queue mode: a service round starts when per / BH_SERVE_DIV lanes wait
-#endif
 #endif
 
 #define BH_NUM_NS lit

@@ -4,7 +4,7 @@ FP32 arithmetic of a trace kernel — the quiet step of hot_iteration — and pr
 against: warp instructions, FMA-pipe units (a packed FFMA2/FMUL2/FADD2 is two), register operand reads
 (two per clock).  The executed-count version of the same numbers comes from tools/ncu_summary.py on a real capture.
 
-    python tools/sass_hot_loop.py [kernel-name-substring] [library]
+    python tools/sass_hot_loop.py [kernel-name-substring] [library] [--list]
       default kernel: fus12trace_kernelILi1ELb0ELi4ELb1E  (FUSED, Cash-Karp, tile mode, 4 CTAs/SM, hole at origin)
 """
 import collections
@@ -40,8 +40,9 @@ def opcode(text):
 
 
 def main():
-    needle = sys.argv[1] if len(sys.argv) > 1 else "fus12trace_kernelILi1ELb0ELi4ELb1E"
-    lib = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "bhusie_b200", "lib", "libbhray.so")
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    needle = args[0] if len(args) > 0 else "fus12trace_kernelILi1ELb0ELi4ELb1E"
+    lib = args[1] if len(args) > 1 else os.path.join(ROOT, "bhusie_b200", "lib", "libbhray.so")
     name, ins = kernel_sass(lib, needle)
     # straight-line runs: split at unpredicated control flow; predicated branches (the never-taken ones) stay inside
     runs, cur = [], []
@@ -66,6 +67,9 @@ def main():
     print(f"quiet step: {best[0][0]}..{best[-1][0]}  {len(best)} instructions, {units} FMA-pipe units, {reads} register operand reads "
           f"({reads / 2:.0f} cycles at 2 per clock)")
     print("  " + "  ".join(f"{op} {c}" for op, c in ops.most_common()))
+    if "--list" in sys.argv:
+        for addr, text in best:
+            print(f"    /*{addr}*/  {text}")
 
 
 if __name__ == "__main__":
