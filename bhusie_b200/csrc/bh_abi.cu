@@ -103,10 +103,6 @@ int bh_ctx_create(int cuda_device, bh_ctx **out)
     if (!c) { set_error("bh_ctx_create: out of host memory"); return BH_ERR_NOMEM; }
     c->device = cuda_device;
     c->sm_count = prop.multiProcessorCount;
-    if (const char *t = getenv("BH_TUNE")) {                 // tuning runs only: "park,serve_div,refill_div"
-        unsigned a = 0, b = 0, d = 0;
-        if (sscanf(t, "%u,%u,%u", &a, &b, &d) == 3) { c->tune[0] = a; c->tune[1] = b; c->tune[2] = d; }
-    }
     *out = c;
     return BH_OK;
 }
@@ -314,7 +310,6 @@ int bh::build_pass_params(bh_ray_pipeline *p, const bh_camera_uniform *camera, c
     P.item_begin = 0;
     P.n_items = (unsigned)P.tiles_x * (unsigned)((p->local_rows + 3) / 4);
     derive_pass_constants(P);
-    P.tune_park = c->tune[0]; P.tune_serve_div = c->tune[1]; P.tune_refill_div = c->tune[2];
     return BH_OK;
 }
 

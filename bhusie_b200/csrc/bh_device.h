@@ -55,7 +55,6 @@ struct PassParams {
     int tiles_x;
     unsigned int tile_rows;          // rows of a tile-mode work item: 4 (8x4 pixels, 32 rays per warp), or 2 / 1 on launches that do not fill the GPU
     float disk_k;                    // 1.0021 * |hole.normal| (+inf when degenerate): fast disk-plane rejection, ray_impl.cuh hot_iteration
-    unsigned tune_park, tune_serve_div, tune_refill_div;   // queue-mode scheduling of trace_kernel (ray_impl.cuh); 0,0,0 = chunk at a time
     float disk_far;                  // 1.001 * accretion_disk_outer (+inf when unusable): a segment that starts farther than
                                      // disk_far + 1.01 h from the hole cannot reach the annulus, ray_impl.cuh hot_iteration
 };

@@ -7,13 +7,6 @@ void set_error(const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what);
 }  // namespace bh
 
-// queue-mode scheduling defaults of trace_kernel (measured: profiles/r2_notes.md)
-#ifndef BH_TUNE_PARK
-#define BH_TUNE_PARK 0u
-#define BH_TUNE_SERVE_DIV 0u
-#define BH_TUNE_REFILL_DIV 0u
-#endif
-
 #define BH_CUDA(call)                                             \
     do {                                                          \
         cudaError_t e_ = (call);                                  \
@@ -29,7 +22,6 @@ struct bh_ctx {
     int models_uploaded = 0;
     int numeric_mode = BH_NUMERIC_FUSED;
     unsigned *async_err = nullptr;       // page-locked word set by a bh_stream_wait that gave up (bh_multi.cu)
-    unsigned tune[3] = { BH_TUNE_PARK, BH_TUNE_SERVE_DIV, BH_TUNE_REFILL_DIV };   // queue-mode scheduling (env BH_TUNE=park,serve_div,refill_div overrides)
 };
 
 struct bh_ray_pipeline {

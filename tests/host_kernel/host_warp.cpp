@@ -166,10 +166,6 @@ extern "C" int bh_host_warp_level(int mode, const void *camera, const void *hole
     std::vector<unsigned> queue((size_t)w * (size_t)local_rows + 1);
     P.stats = stats; P.work = work; P.queue = queue.data();
     derive_pass_constants(P);
-    if (const char *t = getenv("BH_TUNE")) {                 // queue-mode scheduling under test: "park,serve_div,refill_div"
-        unsigned a = 0, b = 0, d = 0;
-        if (sscanf(t, "%u,%u,%u", &a, &b, &d) == 3) { P.tune_park = a; P.tune_serve_div = b; P.tune_refill_div = d; }
-    }
     unsigned pos_bits[3];
     memcpy(pos_bits, P.hole.position, sizeof pos_bits);
     const bool origin = mode == 1 && (pos_bits[0] | pos_bits[1] | pos_bits[2]) == 0u;

@@ -157,13 +157,10 @@ def _assert_level(what, got, ora):
 
 @pytest.mark.parametrize("mode", [0, 1], ids=["literal", "fused"])
 @pytest.mark.parametrize("method", [0, 1], ids=["euler", "rk"])
-@pytest.mark.parametrize("tune", ["0,0,0", "0,2,2", "0,4,4", "1,4,4", "1,2,1", "0,0,2"])
-def test_kernels_as_a_lockstep_warp_pyramid_and_sky(host_warp, oracle, small_scene, small_oracle_scene, mode, method, tune, monkeypatch):
+def test_kernels_as_a_lockstep_warp_pyramid_and_sky(host_warp, oracle, small_scene, small_oracle_scene, mode, method):
     """Three pyramid levels (S_n = 3 S_{n-1} - 2) + sky resolve through the real trace_kernel / classify_kernel / sky_kernel
     control flow, each level fed with the previous one's output, against the oracle: pixels, hit indices, step counts,
-    pixel classes and pass statistics bit for bit — under every queue-mode scheduling of trace_kernel (chunk at a time; lane
-    refill with service rounds; the same with parked literal steps): scheduling must never change a bit."""
-    monkeypatch.setenv("BH_TUNE", tune)
+    pixel classes and pass statistics bit for bit."""
     tex, blob, _ = small_scene
     cam, hole = U.Camera(), U.BlackHole()
     det = U.RayDetails(integration_method=method, model_count=1, time=0.5, angle_division_threshold=0.08)
