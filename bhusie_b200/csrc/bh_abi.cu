@@ -9,7 +9,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <set>
 
 #include "bh_objects.h"
 
@@ -31,6 +33,14 @@ int cuda_fail(cudaError_t e, const char *what)
     return (e == cudaErrorMemoryAllocation) ? BH_ERR_NOMEM
          : (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice) ? BH_ERR_NODEV
          : BH_ERR_CUDA;
+}
+
+static std::mutex g_ctx_mutex;
+static std::set<const bh_ctx *> g_ctx_live;
+bool ctx_alive(const bh_ctx *ctx)
+{
+    std::lock_guard<std::mutex> lock(g_ctx_mutex);
+    return g_ctx_live.count(ctx) != 0;
 }
 
 }  // namespace bh
@@ -103,6 +113,7 @@ int bh_ctx_create(int cuda_device, bh_ctx **out)
     if (!c) { set_error("bh_ctx_create: out of host memory"); return BH_ERR_NOMEM; }
     c->device = cuda_device;
     c->sm_count = prop.multiProcessorCount;
+    { std::lock_guard<std::mutex> lock(g_ctx_mutex); g_ctx_live.insert(c); }
     *out = c;
     return BH_OK;
 }
@@ -110,6 +121,10 @@ int bh_ctx_create(int cuda_device, bh_ctx **out)
 void bh_ctx_destroy(bh_ctx *ctx)
 {
     if (!ctx) return;
+    {
+        std::lock_guard<std::mutex> lock(g_ctx_mutex);
+        if (!g_ctx_live.erase(ctx)) return;              // not (or no longer) one of ours
+    }
     cudaSetDevice(ctx->device);
     for (auto &t : ctx->tex) if (t) cudaFree(t);
     if (ctx->models) cudaFree(ctx->models);
@@ -228,6 +243,7 @@ int bh_ray_pipeline_create(bh_ctx *ctx, uint32_t width, uint32_t height, const b
 void bh_ray_pipeline_destroy(bh_ray_pipeline *p)
 {
     if (!p) return;
+    if (!ctx_alive(p->ctx)) { delete p; return; }        // context destroyed first: nothing of it may be touched
     cudaSetDevice(p->ctx->device);
     if (p->ran) cudaStreamSynchronize(p->last_stream);
     if (p->copy_stream) {
@@ -540,6 +556,7 @@ int bh_sky_pipeline_create_for_frame(bh_ctx *ctx, const void *device_frame_rgba3
 void bh_sky_pipeline_destroy(bh_sky_pipeline *s)
 {
     if (!s) return;
+    if (!ctx_alive(s->ctx)) { delete s; return; }
     cudaSetDevice(s->ctx->device);
     if (s->ran) cudaStreamSynchronize(s->last_stream);
     if (s->own_out) cudaFree(s->own_out);
@@ -633,6 +650,7 @@ int bh_post_pass_create(bh_ctx *ctx, bh_post_kind kind, uint32_t out_w, uint32_t
 void bh_post_pass_destroy(bh_post_pass *p)
 {
     if (!p) return;
+    if (!ctx_alive(p->ctx)) { delete p; return; }
     cudaSetDevice(p->ctx->device);
     if (p->ran) cudaStreamSynchronize(p->last_stream);
     if (p->out) cudaFree(p->out);

@@ -199,7 +199,7 @@ int bh_host_frame_create(bh_ctx *ctx, const char *shm_name, size_t nbytes, int c
 void bh_host_frame_destroy(bh_host_frame *hf, int unlink_name)
 {
     if (!hf) return;
-    if (hf->registered) { cudaSetDevice(hf->ctx->device); cudaHostUnregister(hf->base); }
+    if (hf->registered) { if (ctx_alive(hf->ctx)) cudaSetDevice(hf->ctx->device); cudaHostUnregister(hf->base); }
     if (hf->base) munmap(hf->base, hf->map_bytes);
     if (unlink_name) { if (hf->is_path) unlink(hf->name); else shm_unlink(hf->name); }
     delete hf;
@@ -362,6 +362,8 @@ int bh_frame_multi_create(bh_ctx *const *ctxs, uint32_t n_devices, const bh_fram
 void bh_frame_multi_destroy(bh_frame_multi *fm)
 {
     if (!fm) return;
+    for (uint32_t d = 0; d < fm->n; ++d)
+        if (!ctx_alive(fm->ctx[d])) { delete fm; return; }       // a context went first: leak rather than touch it
     for (uint32_t d = 0; d < fm->n; ++d) {
         cudaSetDevice(fm->ctx[d]->device);
         if (fm->stream[d]) cudaStreamSynchronize(fm->stream[d]);

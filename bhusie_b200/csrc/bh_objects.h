@@ -5,6 +5,10 @@
 namespace bh {
 void set_error(const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what);
+// true while `ctx` is a context created by bh_ctx_create and not yet destroyed.  The destroy functions of pipelines / passes
+// ask before they touch their context: a host that drops objects in the wrong order (bh_ctx_destroy first) then leaks the
+// object's device memory instead of dereferencing a freed context.
+bool ctx_alive(const struct ::bh_ctx *ctx);
 }  // namespace bh
 
 #define BH_CUDA(call)                                             \

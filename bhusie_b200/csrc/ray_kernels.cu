@@ -239,6 +239,8 @@ static cudaError_t launch_trace_mode(const PassParams &p, const LaunchConfig &cf
 
 cudaError_t launch_ray_pass(const PassParams &p, const LaunchConfig &cfg, cudaStream_t stream)
 {
+    (void)cudaGetLastError();          // a stale error of an unrelated earlier call is not this launch's
+
     cudaError_t e = cudaMemsetAsync(p.work, 0, sizeof(unsigned) * kWorkCount, stream);
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(p.stats, 0, sizeof(unsigned long long) * kStatCount, stream);
@@ -258,6 +260,8 @@ cudaError_t launch_ray_pass(const PassParams &p, const LaunchConfig &cfg, cudaSt
 
 cudaError_t launch_trace_range(const PassParams &p, const LaunchConfig &cfg, bool reset_stats, cudaStream_t stream)
 {
+    (void)cudaGetLastError();          // a stale error of an unrelated earlier call is not this launch's
+
     cudaError_t e = cudaMemsetAsync(p.work, 0, sizeof(unsigned) * kWorkCount, stream);
     if (e != cudaSuccess) return e;
     if (reset_stats) {
@@ -270,6 +274,8 @@ cudaError_t launch_trace_range(const PassParams &p, const LaunchConfig &cfg, boo
 
 cudaError_t launch_sky_pass(const SkyParams &s, const LaunchConfig &cfg, cudaStream_t stream)
 {
+    (void)cudaGetLastError();          // a stale error of an unrelated earlier call is not this launch's
+
     unsigned grid = (unsigned)((s.n_pixels + 255) / 256);
     const unsigned cap = (unsigned)cfg.sm_count * 8u;
     if (grid > cap) grid = cap;
@@ -281,6 +287,8 @@ cudaError_t launch_sky_pass(const SkyParams &s, const LaunchConfig &cfg, cudaStr
 
 cudaError_t launch_post_pass(int kind, const PostParams &p, const LaunchConfig &cfg, cudaStream_t stream)
 {
+    (void)cudaGetLastError();          // a stale error of an unrelated earlier call is not this launch's
+
     const dim3 grid((unsigned)((p.w + 31) / 32), (unsigned)((p.h + 7) / 8));
     const bool lit_mode = cfg.numeric_mode == BH_NUMERIC_LITERAL;
     switch (kind) {

@@ -191,7 +191,9 @@ int  bh_ray_pipeline_read(bh_ray_pipeline *p, float *host_rgba32f, int32_t *host
 typedef struct bh_pass_stats {              /* totals of the last pass (waits for it) */
     uint64_t ray_steps;                     /* integrator calls: next_ray_rk / next_ray_euler (ray.wgsl:525-531) */
     uint64_t px_traced, px_copied, px_interp;
-    uint64_t node_visits, tri_tests;        /* BVH inner-node visits / hit_triangle calls */
+    uint64_t node_visits, tri_tests;        /* BVH inner-node visits / hit_triangle calls actually made: the walk is bounded by the
+                                             * relativity-sphere hit when there is one (a triangle behind it is discarded anyway,
+                                             * ray.wgsl:562), so these can be below the literal traversal's counts */
     uint64_t tex_samples;                   /* bilinear samples taken (disk, LUT, sky) */
     uint64_t rk_reject;                     /* RK steps whose error norm exceeded 1 (reference would spin; Q5) */
     uint64_t stack_overflow;                /* BVH pushes beyond the reference's 19-entry stack (Q16) */

@@ -85,7 +85,8 @@ def check_frame(oracle, osc, ctx, name, dev, st, w, h, cam, hole, det, prev=None
         assert np.array_equal(dev["cls"], ora.cls), f"{name}: classes differ"
     c = ora.counters
     assert (st["ray_steps"], st["px_traced"], st["px_copied"], st["px_interp"]) == (c["steps"], c["px_traced"], c["px_copied"], c["px_interp"])
-    assert (st["node_visits"], st["tri_tests"], st["tex_samples"]) == (c["node_visits"], c["tri_tests"], c["tex_samples"])
+    assert st["tex_samples"] == c["tex_samples"]
+    assert st["node_visits"] <= c["node_visits"] and st["tri_tests"] <= c["tri_tests"]      # sphere-bounded BVH walk: never more work
     assert st["rk_reject"] == 0 and st["stack_overflow"] == 0
     if neutral_key is not None:
         strict, shadow, probe = neutral(oracle, osc, neutral_key, w, h, cam, hole, det, prev)
@@ -99,8 +100,9 @@ def check_frame(oracle, osc, ctx, name, dev, st, w, h, cam, hole, det, prev=None
         n_px = rep["pixels"]
         assert rep["outliers"] <= max(MAX_OUTLIER_FRAC[mode] * n_px, 32), (name, rep)
         assert rep["outlier_frac_well_conditioned"] * n_px <= max(MAX_WELL_CONDITIONED_OUTLIER_FRAC[mode] * n_px, 8), (name, rep)
-        assert rep["hit_index_equal_frac"] >= 0.9995, (name, rep)        # north star: hit indices bit-exact — they are, vs the mode's flavour;
-        assert rep["step_count_equal_frac"] >= 0.999, (name, rep)        # vs libm a few edge pixels flip
+        # north star: hit indices bit-exact — they are, vs the mode's flavour; vs libm a few edge pixels flip
+        assert (1.0 - rep["hit_index_equal_frac"]) * n_px <= max(5e-4 * n_px, 16), (name, rep)
+        assert (1.0 - rep["step_count_equal_frac"]) * n_px <= max(1e-3 * n_px, 48), (name, rep)
     return ora
 
 

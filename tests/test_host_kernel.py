@@ -89,8 +89,10 @@ def test_device_source_on_cpu_matches_oracle(host_kernel, oracle, small_scene, s
     same = bits(rgba) == bits(ora.rgba)
     assert same.all(), f"{case}: {(~same).mean():.3%} of RGBA words differ"
     assert np.array_equal(hit, ora.hit) and np.array_equal(steps, ora.steps)
-    for k in ("steps", "px_traced", "node_visits", "tri_tests", "tex_samples", "rk_reject", "stack_overflow"):
+    for k in ("steps", "px_traced", "tex_samples", "rk_reject", "stack_overflow"):
         assert st[k] == ora.counters[k], (k, st[k], ora.counters[k])
+    for k in ("node_visits", "tri_tests"):              # the BVH walk is bounded by the sphere hit (trace_model): it may do LESS work
+        assert st[k] <= ora.counters[k] and (st[k] > 0) == (ora.counters[k] > 0), (k, st[k], ora.counters[k])
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -152,7 +154,10 @@ def _assert_level(what, got, ora):
     assert np.array_equal(steps, ora.steps), what
     assert np.array_equal(cls, ora.cls), what
     for k in STAT_NAMES[:7] + ("rk_reject", "stack_overflow"):
-        assert st[k] == ora.counters[k], (what, k, st[k], ora.counters[k])
+        if k in ("node_visits", "tri_tests"):       # the BVH walk is bounded by the sphere hit (trace_model): it may do LESS work
+            assert st[k] <= ora.counters[k] and (st[k] > 0) == (ora.counters[k] > 0), (what, k, st[k], ora.counters[k])
+        else:
+            assert st[k] == ora.counters[k], (what, k, st[k], ora.counters[k])
 
 
 @pytest.mark.parametrize("mode", [0, 1], ids=["literal", "fused"])
