@@ -348,18 +348,11 @@ def run_ours(args):
         for _ in range(steps):
             flush.zero_()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            if fr.exchange == "p2p" and fr.rank != 0:
-                fr.render_local(cam, hole, det, stream)     # (begins with the wait for rank 0's "consumed" flag: not kernel time)
-                a = b = None
-            else:
-                a.record(stream)
-                fr.render_local(cam, hole, det, stream)
-                b.record(stream)
+            fr.render_local(cam, hole, det, stream, events=(a, b))      # events around the ray kernel proper (after any flag wait)
             fr.gather(stream)
             fr.resolve_sky(stream)
             fr.consumed(stream)
-            if a is not None:
-                k0.append(a); k1.append(b)
+            k0.append(a); k1.append(b)
         e1.record(stream)
         barrier()
         ctx.check_async()
@@ -404,7 +397,13 @@ def run_ours(args):
     t = torch.tensor([elapsed_ms, kernel_ms], dtype=torch.float64, device="cuda")
     s = torch.tensor([stats[k] for k in STAT_KEYS], dtype=torch.float64, device="cuda")
     s_local = s.clone()
+    per_rank = None
     if world > 1:
+        # every rank's own share: ray-steps, mean kernel time, elapsed time
+        mine = torch.tensor([float(stats["ray_steps"]), kernel_ms, elapsed_ms], dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"ray_steps": [int(x[0]) for x in allr], "kernel_ms": [float(x[1]) for x in allr], "elapsed_ms": [float(x[2]) for x in allr]}
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
     elapsed_ms = float(t[0])
@@ -579,6 +578,7 @@ def run_ours(args):
                               "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz (non-tensor FP32, BASELINE.md §2)"},
         }
         if world > 1:
+            line["per_rank"] = per_rank
             line["exchange_bit_identical"] = exchange_bit_identical
             line["e2e"]["host_frame_equals_device_frame"] = e2e_matches_device
         if c4 is not None:

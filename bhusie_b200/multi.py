@@ -161,14 +161,19 @@ class TiledFrame:
             t = self.frame_tensor()
             self.sky = SkyPipeline(ctx, None, sky_format, frame=(t.data_ptr(), width, height))
 
-    def render_local(self, camera, black_hole, details, stream=None):
-        """Enqueues this rank's share on `stream`: the replicated coarse levels, then its bands of the last level."""
+    def render_local(self, camera, black_hole, details, stream=None, events=None):
+        """Enqueues this rank's share on `stream`: the replicated coarse levels, then its bands of the last level.
+        `events` = (start, end): two events recorded around the ray passes proper (after the wait for rank 0)."""
         self._seq += 1
         if self.exchange == "p2p" and self.rank != 0 and self._seq > 1:
             # this rank's kernel writes into rank 0's frame: not before rank 0 has consumed the previous one
             self.ctx.stream_wait(self._flags + 4 * CONSUMED_SLOT, 1, self._seq - 1, WAIT_TIMEOUT_MS, stream)
+        if events is not None:
+            events[0].record(stream)
         for rp in self.levels:
             rp.pass_(camera, black_hole, details, stream)
+        if events is not None:
+            events[1].record(stream)
         if self.exchange == "p2p" and self.rank != 0:
             self.ctx.stream_signal(self._flags + 4 * self.rank, self._seq, stream)
 

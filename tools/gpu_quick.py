@@ -57,6 +57,22 @@ def main():
                                           "ray_steps": st["ray_steps"], "local_rows": t.local_rows}
         print(f"tiled 1 of {world}", out[f"tiled_rank1_of_{world}"], flush=True)
         t.close()
+    # the same with a cold L2 (what bench.py's flush before every step does): events around the pass only
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for world in (1, 8):
+        t = P.RayPipeline(ctx, 3840, 2160)
+        if world > 1:
+            t.set_tiling(8, 1, world)
+        tot = 0.0
+        for _ in range(6):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(s); t.pass_(cam, hole, det, s); b.record(s)
+            torch.cuda.synchronize()
+            tot += a.elapsed_time(b)
+        out[f"cold_l2_rank1_of_{world}"] = {"ms": tot / 6}
+        print(f"cold L2, 1 of {world}", out[f"cold_l2_rank1_of_{world}"], flush=True)
+        t.close()
     small = P.RayPipeline(ctx, 3840, 272)          # the same pixel count as one rank of 8, as a plain frame of its own
     ms = timed(lambda: small.pass_(cam, hole, det, s), s, 2, 8)
     out["plain_3840x272"] = {"ms": ms, "ray_steps": small.stats()["ray_steps"], "gsteps_per_s": small.stats()["ray_steps"] / ms / 1e6}
