@@ -313,6 +313,7 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        host_group = dist.new_group(backend="gloo")       # host-side barrier: ranks can wait without a kernel spinning on their GPU
 
     W, H = args.width, args.height
     tex, tex_src, blob, mesh_src, mesh_info = load_scene()
@@ -495,11 +496,15 @@ def run_ours(args):
 
     # ---------------- bh_frame_multi (one process, one host thread, all N devices) checked by rank 0 while the others idle
     frame_multi = None
-    if world > 1 and rank == 0 and not args.no_frame_multi:
-        try:
-            frame_multi = frame_multi_block(P, U, torch, ctx, tex, blob, world, W, H, args.band_rows, cam, hole, det)
-        except Exception as ex:               # a diagnostic, not the measurement: never lose the line over it
-            frame_multi = {"error": str(ex)[:300]}
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier(group=host_group)
+        if rank == 0 and not args.no_frame_multi:
+            try:
+                frame_multi = frame_multi_block(P, U, torch, ctx, tex, blob, world, W, H, args.band_rows, cam, hole, det)
+            except Exception as ex:               # a diagnostic, not the measurement: never lose the line over it
+                frame_multi = {"error": str(ex)[:300]}
+        dist.barrier(group=host_group)            # the other ranks wait on the host: their GPUs are idle for rank 0's contexts
     barrier()
 
     if rank == 0:
