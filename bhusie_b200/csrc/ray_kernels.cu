@@ -77,6 +77,10 @@ constexpr int kTopBytes = kTopHeaderBytes + kTopNodes * 32;
 #ifndef BH_SHADE_BATCH
 #define BH_SHADE_BATCH 8
 #endif
+// ... or one crossing has waited this many warp votes (two steps each)
+#ifndef BH_SHADE_PATIENCE
+#define BH_SHADE_PATIENCE 8
+#endif
 
 #define BH_NUM_NS lit
 #define BH_FUSED 0
