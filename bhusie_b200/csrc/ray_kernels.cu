@@ -73,9 +73,10 @@ constexpr int kTopBytes = kTopHeaderBytes + kTopNodes * 32;
 #ifndef BH_OCC_EULER
 #define BH_OCC_EULER 4
 #endif
-// lanes of a warp that must wait for disk shading before the hot phase is interrupted for them (1 = serve every crossing at once)
+// lanes of a 32-ray warp that must wait for disk shading before the hot phase is interrupted for them (1 = serve every crossing at
+// once).  Reference frame, RK: 4 -> 2.72 ms, 8 -> 2.59, 16 -> 2.53 (profiles/r2_10_*_quick.json); narrower warps scale it down.
 #ifndef BH_SHADE_BATCH
-#define BH_SHADE_BATCH 8
+#define BH_SHADE_BATCH 16
 #endif
 // ... or one crossing has waited this many warp votes (two steps each)
 #ifndef BH_SHADE_PATIENCE

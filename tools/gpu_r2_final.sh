@@ -4,7 +4,7 @@
 cd "$(dirname "$0")/.."
 T=${1:-r2_final}
 mkdir -p gpurun_out
-for V in sb4 sb16 sp4 sp16 sb4sp4; do
+for V in sb24 sb32 sb32sp12; do
   if [ -f bhusie_b200/lib/libbhray_${V}.so ]; then
     BHRAY_LIB=$PWD/bhusie_b200/lib/libbhray_${V}.so timeout 300 python tools/gpu_quick.py ${T}_${V} > gpurun_out/${T}_${V}_quick.log 2>&1
     echo "== ${V}"; grep -E "^c3_rk_fused|^pyramid" gpurun_out/${T}_${V}_quick.log
