@@ -196,3 +196,41 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_kernel_constants_are_refused_when_stale(tmp_path, monkeypatch):
+    """bench.py's issue-rate roofline uses per-warp-step counts from a committed ncu capture; they only count when the capture
+    was taken from the kernel source this build is made of (bhusie_b200.build.kernel_source_hash)."""
+    import bench
+    from bhusie_b200 import build as B
+    h = B.kernel_source_hash()
+    assert len(h) == 16 and h == B.kernel_source_hash()
+    prof = tmp_path / "profiles"
+    prof.mkdir()
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    (prof / "trace_kernel_dram.json").write_text(json.dumps({"fused": {"source_hash": h, "warp_inst_per_warp_step": 190.0}}))
+    pj, state = bench.kernel_constants("fused")
+    assert state == "current" and pj["warp_inst_per_warp_step"] == 190.0
+    (prof / "trace_kernel_dram.json").write_text(json.dumps({"fused": {"source_hash": "0" * 16, "warp_inst_per_warp_step": 190.0}}))
+    pj, state = bench.kernel_constants("fused")
+    assert pj == {} and state.startswith("stale")
+    pj, state = bench.kernel_constants("literal")
+    assert pj == {}
+
+
+def test_model_validate_on_the_host():
+    """bh_model_validate (pure host code): a blob built by the library passes; corrupt indices, a root that is its own child and
+    lookup entries beyond the triangle array are refused; the empty model the reference starts with is accepted."""
+    from bhusie_b200 import assets
+    blob, info = P.model_from_arrays(*assets.uv_sphere(6, 8, radius=2.0))
+    P.validate_model(blob)
+    tri0 = int(blob[U.MU_LOOKUP:U.MU_LOOKUP + 4].view(np.int32)[0])
+    for off, val in ((U.MU_NODES + 12, 10 ** 6), (U.MU_NODES + 12, 0), (U.MU_TRIANGLES + 24 * tri0, 600000),
+                     (U.MU_TRIANGLES + 24 * tri0 + 12, -5), (U.MU_LOOKUP, 1 << 20)):
+        bad = blob.copy()
+        bad[off:off + 4].view(np.int32)[0] = val
+        with pytest.raises(_lib.BhError) as e:
+            P.validate_model(bad)
+        assert e.value.code == -22
+    empty, _ = P.model_from_arrays(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32), np.zeros((0, 6), np.int32))
+    P.validate_model(empty)
