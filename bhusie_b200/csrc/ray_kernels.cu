@@ -74,13 +74,15 @@ constexpr int kTopBytes = kTopHeaderBytes + kTopNodes * 32;
 #define BH_OCC_EULER 4
 #endif
 // lanes of a 32-ray warp that must wait for disk shading before the hot phase is interrupted for them (1 = serve every crossing at
-// once).  Reference frame, RK: 4 -> 2.72 ms, 8 -> 2.59, 16 -> 2.53 (profiles/r2_10_*_quick.json); narrower warps scale it down.
+// once).  Reference frame, RK: 4 -> 2.72 ms, 8 -> 2.59, 16 -> 2.53, 24 -> 2.46, 32 -> 2.43 (profiles/r2_10_*, r2_11_*_quick.json): in
+// effect a crossing is shaded when nobody steps any more or when it has waited BH_SHADE_PATIENCE votes (8 -> 2.43 ms, 12 -> 2.45 ms,
+// Euler 2.00 -> 1.98 ms, 4K grid 6.50 -> 6.47 ms); narrower warps scale the batch down.
 #ifndef BH_SHADE_BATCH
-#define BH_SHADE_BATCH 16
+#define BH_SHADE_BATCH 32
 #endif
 // ... or one crossing has waited this many warp votes (two steps each)
 #ifndef BH_SHADE_PATIENCE
-#define BH_SHADE_PATIENCE 8
+#define BH_SHADE_PATIENCE 12
 #endif
 
 #define BH_NUM_NS lit

@@ -66,8 +66,8 @@ static inline void mbar_wait(unsigned long long *, unsigned) {}
 constexpr int kTopNodes = 256;
 constexpr int kTopHeaderBytes = 64;
 constexpr int kTopBytes = kTopHeaderBytes + kTopNodes * 32;
-#define BH_SHADE_BATCH 16
-#define BH_SHADE_PATIENCE 8
+#define BH_SHADE_BATCH 32
+#define BH_SHADE_PATIENCE 12
 #define BH_NUM_NS lit
 #define BH_FUSED 0
 #include "../../bhusie_b200/csrc/ray_impl.cuh"
