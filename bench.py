@@ -96,9 +96,10 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.time()] + [c.strip() for c in line.split(",")][1:])
 
-    def stop(self) -> dict:
+    def stop(self, t0: float | None = None, t1: float | None = None) -> dict:
+        """Median SM clock and throttle reasons of the samples taken in [t0, t1] (wall clock); of all samples if fewer than 3 are."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -106,8 +107,13 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        rows, window = self.rows, "whole run (warm-up + timed regions)"
+        if t0 is not None:
+            inside = [r for r in self.rows if t0 <= r[0] <= t1]
+            if len(inside) >= 3:
+                rows, window = inside, "timed region"
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
                 for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
@@ -116,7 +122,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def load_scene():
@@ -324,6 +330,9 @@ def run_ours(args):
     cam, hole = U.Camera(), U.BlackHole()
     det = U.RayDetails(integration_method=1, model_count=1)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                 # nvidia-smi takes a few hundred ms to deliver its first sample: started well before the timed region
     frame = TiledFrame(ctx, W, H, rank, world, band_rows=args.band_rows, exchange=args.exchange)
     stream = torch.cuda.current_stream()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -376,24 +385,12 @@ def run_ours(args):
         barrier()
 
     # ---------------- device-resident timing (FUSED unless --numeric-mode literal)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()                 # sampled from the warm-up on: at N=8 the timed region itself is < 100 ms
     for _ in range(args.warmup):
         step_device()
     barrier()
-    n_warm_samples = len(sampler.rows)
+    t_wall0 = time.time()
     elapsed_ms, kernel_ms = timed_steps(frame, args.steps, 0)
-    if rank == 0:
-        if len(sampler.rows) - n_warm_samples >= 3:
-            sampler.rows = sampler.rows[n_warm_samples:]      # enough samples inside the timed region proper
-            window = "timed region"
-        else:
-            window = "warm-up + timed region (timed region shorter than 3 sampling periods)"
-        clocks = sampler.stop()
-        clocks["window"] = window
-    else:
-        clocks = None
+    t_wall1 = time.time()
     stats = frame.pipeline.stats()
     t = torch.tensor([elapsed_ms, kernel_ms], dtype=torch.float64, device="cuda")
     s = torch.tensor([stats[k] for k in STAT_KEYS], dtype=torch.float64, device="cuda")
@@ -423,6 +420,7 @@ def run_ours(args):
     ms_other = float(lt[0]) / lit_steps
     ctx.set_numeric_mode(mode)
     other_name = "literal" if other == P.NUMERIC_LITERAL else "fused"
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
 
     # ---------------- end-to-end timing: host buffers, H2D model blob + pass with the pixels stored straight into the host frame
     pinned_model = torch.from_numpy(blob).pin_memory()
