@@ -85,6 +85,11 @@ constexpr int kTopBytes = kTopHeaderBytes + kTopNodes * 32;
 #define BH_SHADE_PATIENCE 12
 #endif
 
+// one-copy hot loop in queue-mode kernels (see trace_warp in ray_impl.cuh; 0 = the two-copy loop everywhere)
+#ifndef BH_QUEUE_COMPACT
+#define BH_QUEUE_COMPACT 1
+#endif
+
 #define BH_NUM_NS lit
 #define BH_FUSED 0
 #include "ray_impl.cuh"

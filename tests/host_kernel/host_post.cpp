@@ -68,6 +68,7 @@ constexpr int kTopHeaderBytes = 64;
 constexpr int kTopBytes = kTopHeaderBytes + kTopNodes * 32;
 #define BH_SHADE_BATCH 32
 #define BH_SHADE_PATIENCE 12
+#define BH_QUEUE_COMPACT 1
 #define BH_NUM_NS lit
 #define BH_FUSED 0
 #include "../../bhusie_b200/csrc/ray_impl.cuh"
