@@ -343,31 +343,36 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def step_device(fr=frame):
-        flush.zero_()                       # L2 flush (256 MiB > 126 MB L2), inside the timed region
+        flush.zero_()                       # L2 flush (256 MiB > 126 MB L2)
         fr.render(cam, hole, det, stream)   # local bands; N > 1: peer stores into rank 0's frame + flag wait (or NCCL gather)
         fr.consumed(stream)
 
     def timed_steps(fr, steps, warmup):
-        """(elapsed ms over `steps`, mean kernel ms of this rank) — device events on the launching stream."""
+        """(ms summed over `steps` step intervals, the same including the L2 flushes between them, mean kernel ms of this rank) —
+        device events on the launching stream.  A step's interval opens after the flush that precedes it (the flush is the
+        timing hygiene BETWEEN iterations, not part of the pass) and closes after the frame is complete on rank 0."""
         for _ in range(warmup):
             step_device(fr)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k0, k1 = [], []
+        k0, k1, s0, s1 = [], [], [], []
         e0.record(stream)
         for _ in range(steps):
             flush.zero_()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            sa, sb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            sa.record(stream)
             fr.render_local(cam, hole, det, stream, events=(a, b))      # events around the ray kernel proper (after any flag wait)
             fr.gather(stream)
             fr.resolve_sky(stream)
+            sb.record(stream)
             fr.consumed(stream)
-            k0.append(a); k1.append(b)
+            k0.append(a); k1.append(b); s0.append(sa); s1.append(sb)
         e1.record(stream)
         barrier()
         ctx.check_async()
         kernel = float(np.mean([a.elapsed_time(b) for a, b in zip(k0, k1)])) if k0 else 0.0
-        return e0.elapsed_time(e1), kernel
+        return float(sum(a.elapsed_time(b) for a, b in zip(s0, s1))), e0.elapsed_time(e1), kernel
 
     # ---------------- N > 1: the assembled frame must be bit-identical to a single-GPU render (in the warm-up, not timed)
     exchange_bit_identical = None
@@ -389,10 +394,10 @@ def run_ours(args):
         step_device()
     barrier()
     t_wall0 = time.time()
-    elapsed_ms, kernel_ms = timed_steps(frame, args.steps, 0)
+    elapsed_ms, elapsed_flush_ms, kernel_ms = timed_steps(frame, args.steps, 0)
     t_wall1 = time.time()
     stats = frame.pipeline.stats()
-    t = torch.tensor([elapsed_ms, kernel_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([elapsed_ms, kernel_ms, elapsed_flush_ms], dtype=torch.float64, device="cuda")
     s = torch.tensor([stats[k] for k in STAT_KEYS], dtype=torch.float64, device="cuda")
     s_local = s.clone()
     per_rank = None
@@ -404,7 +409,7 @@ def run_ours(args):
         per_rank = {"ray_steps": [int(x[0]) for x in allr], "kernel_ms": [float(x[1]) for x in allr], "elapsed_ms": [float(x[2]) for x in allr]}
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
-    elapsed_ms = float(t[0])
+    elapsed_ms, elapsed_flush_ms = float(t[0]), float(t[2])
     total = dict(zip(STAT_KEYS, (int(x) for x in s.tolist())))
     ms_per_step = elapsed_ms / args.steps
     value = total["ray_steps"] / (ms_per_step * 1e-3) / 1e6
@@ -413,7 +418,7 @@ def run_ours(args):
     other = P.NUMERIC_LITERAL if mode == P.NUMERIC_FUSED else P.NUMERIC_FUSED
     ctx.set_numeric_mode(other)
     lit_steps = max(3, args.steps // 2)
-    lit_ms, _ = timed_steps(frame, lit_steps, 3)
+    lit_ms, _, _ = timed_steps(frame, lit_steps, 3)
     lt = torch.tensor([lit_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(lt, op=dist.ReduceOp.MAX)
@@ -422,35 +427,66 @@ def run_ours(args):
     other_name = "literal" if other == P.NUMERIC_LITERAL else "fused"
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
 
-    # ---------------- end-to-end timing: host buffers, H2D model blob + pass with the pixels stored straight into the host frame
+    # ---------------- end-to-end timing: host buffers, H2D model blob + pass with the pixels stored straight into the host frame.
+    # TWO frames in flight (the renderer's usual double buffering): frame k+1's inputs go up while frame k is traced, each frame on
+    # its own context (model buffer), stream and host frame; a frame's buffers are reused only after it was finished and read.
+    # `e2e_serial` is the same loop with ONE frame in flight (upload, pass, wait — what round 1 reported as e2e).
     pinned_model = torch.from_numpy(blob).pin_memory()
-    if world == 1:
-        host_frame = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
-        hframe = None
-    else:
-        hframe = HostTiledFrame(ctx, W, H, rank, world, band_rows=args.band_rows)
-        host_frame = None
-
-    def step_e2e(header_only=False):
-        flush.zero_()
-        if header_only:
-            ctx.set_model_header(0, (-10.0, 0.0, 30.0), 1)        # what the UI can change per frame (ui/model_settings.rs:39-48): 16 bytes
-        else:
-            ctx.upload_models_async(pinned_model.data_ptr(), pinned_model.numel(), stream)
+    ctx_b = P.Context(local_rank, numeric_mode=mode)
+    ctx_b.set_textures(tex)
+    ctx_b.upload_models(blob)
+    stream_b = torch.cuda.Stream()
+    lanes = []                                            # [context, stream, host frame (N=1) | HostTiledFrame (N>1), ray pipeline]
+    for i, (c, st) in enumerate(((ctx, stream), (ctx_b, stream_b))):
         if world == 1:
-            frame.pipeline.pass_to_host(cam, hole, det, host_frame.data_ptr(), args.e2e_chunks, stream)
-            frame.pipeline.sync()
+            hf = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
+            rp = frame.pipeline if i == 0 else P.RayPipeline(c, W, H)
+            lanes.append([c, st, hf, rp])
         else:
-            hframe.render(cam, hole, det, stream)        # every rank: own bands -> the shared host frame over its own PCIe link
-            hframe.consumed()
+            hf = HostTiledFrame(c, W, H, rank, world, band_rows=args.band_rows,
+                                name=f"/bhframe_{os.environ.get('MASTER_PORT', '0')}_{W}x{H}_{i}")
+            lanes.append([c, st, hf, hf.pipeline])
+    probe = [0.0]
 
-    def timed_e2e(header_only):
-        for _ in range(max(1, min(args.warmup, 2))):
-            step_e2e(header_only)
+    def e2e_enqueue(lane, header_only):
+        c, st, hf, rp = lane
+        with torch.cuda.stream(st):
+            flush.zero_()
+        if header_only:
+            c.set_model_header(0, (-10.0, 0.0, 30.0), 1)          # what the UI can change per frame (ui/model_settings.rs:39-48): 16 bytes
+        else:
+            c.upload_models_async(pinned_model.data_ptr(), pinned_model.numel(), st)
+        if world == 1:
+            rp.pass_to_host(cam, hole, det, hf.data_ptr(), args.e2e_chunks, st)
+        else:
+            hf.enqueue(cam, hole, det, st)                        # own bands -> the shared host frame over this rank's own PCIe link
+
+    def e2e_finish(lane):
+        c, st, hf, rp = lane
+        if world == 1:
+            rp.sync()
+            probe[0] += float(hf[H // 2, W // 2, 0])              # the step's result, read on the host
+        else:
+            hf.finish()
+            if rank == 0:
+                probe[0] += float(hf.frame_array()[H // 2, W // 2, 0])
+            hf.consumed()
+
+    def timed_e2e(header_only, in_flight):
+        def loop(n):
+            pending = []
+            for k in range(n):
+                lane = lanes[k % in_flight]
+                e2e_enqueue(lane, header_only)
+                pending.append(lane)
+                if len(pending) == in_flight:
+                    e2e_finish(pending.pop(0))
+            while pending:
+                e2e_finish(pending.pop(0))
+        loop(max(2, min(args.warmup, 4)))
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step_e2e(header_only)
+        loop(args.steps)
         barrier()
         dt = time.perf_counter() - t0
         te = torch.tensor([dt], dtype=torch.float64, device="cuda")
@@ -458,15 +494,18 @@ def run_ours(args):
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         return float(te[0])
 
-    e2e_s = timed_e2e(False)
-    e2e_hdr_s = timed_e2e(True)
+    e2e_serial_s = timed_e2e(False, 1)
+    e2e_hdr_s = timed_e2e(True, 1)
+    e2e_s = timed_e2e(False, 2)
     e2e_value = total["ray_steps"] * args.steps / e2e_s / 1e6
     if world > 1:
         step_device()                       # the device frame in the headline numeric mode again, to compare the host frame with
         barrier()
     if rank == 0:
-        hf = host_frame.numpy() if world == 1 else hframe.frame_array()
+        hf = lanes[0][2].numpy() if world == 1 else lanes[0][2].frame_array()
+        hf_b = lanes[1][2].numpy() if world == 1 else lanes[1][2].frame_array()
         checksum = float(hf[::97, ::89].astype(np.float64).sum())
+        e2e_lanes_equal = bool(np.array_equal(np.ascontiguousarray(hf).view(np.uint32), np.ascontiguousarray(hf_b).view(np.uint32)))
         e2e_matches_device = None
         if world > 1:
             dev_frame = frame.frame_tensor().cpu().numpy()
@@ -479,7 +518,7 @@ def run_ours(args):
     if world > 1 and (args.c4 == "on" or (args.c4 == "auto" and world == 8)):
         f8 = TiledFrame(ctx, 7680, 4320, rank, world, band_rows=args.band_rows, exchange=args.exchange)
         c4_steps = max(3, min(args.steps, 8))
-        c4_ms, _ = timed_steps(f8, c4_steps, 3)
+        c4_ms, _, _ = timed_steps(f8, c4_steps, 3)
         st8 = f8.pipeline.stats()
         v8 = torch.tensor([c4_ms, float(st8["ray_steps"])], dtype=torch.float64, device="cuda")
         vmax = v8.clone()
@@ -543,7 +582,7 @@ def run_ours(args):
             roofline["constants"] = pj_state
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "fps": 1000.0 / ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "ms_per_step": ms_per_step, "ms_per_step_incl_flush": elapsed_flush_ms / args.steps, "fps": 1000.0 / ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": f"synthetic (default camera/black hole uniforms); textures={tex_src}; mesh={mesh_src}",
             "numeric_mode": args.numeric_mode,
             f"value_{other_name}": total["ray_steps"] / (ms_other * 1e-3) / 1e6, f"ms_per_step_{other_name}": ms_other,
@@ -553,7 +592,8 @@ def run_ours(args):
                        "exchange": {"p2p": "ray kernel stores finished pixels directly into rank 0's frame over NVLink (CUDA IPC peer memory); ordering by "
                                            "stream-ordered flag stores / waits in that memory (no collective in the frame loop)",
                                     "nccl": "NCCL gather of compact band buffers to rank 0 + de-interleave copy", "none": "single GPU"}[frame.exchange],
-                       "l2_flush": "256 MiB memset before every step, inside the timed region",
+                       "l2_flush": "256 MiB memset before every step, between the per-step event pairs that are summed (ms_per_step_incl_flush: one event "
+                                   "pair around all steps, flushes included)",
                        "ray_steps_per_frame": total["ray_steps"],
                        "numerics": ("FUSED: explicit fma contraction + reciprocal-multiply, det-math transcendentals (bit-exact vs oracle 'fused')"
                                     if mode == P.NUMERIC_FUSED else
@@ -561,15 +601,20 @@ def run_ours(args):
                        "kernel_source_hash": B.kernel_source_hash()},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pinned_model.numel() + 196) * world,
                     "d2h_bytes_per_step": int(W * H * 16), "ms_per_step": 1000.0 * e2e_s / args.steps, "fps": args.steps / e2e_s,
-                    "frame_checksum": checksum,
-                    "path": ("bh_ctx_upload_models_async + bh_ray_pipeline_pass_to_host("
-                             + ("zero-copy: pixel stores land in the pinned host frame over PCIe during the pass" if args.e2e_chunks == 0
-                                else f"{args.e2e_chunks} bands, D2H overlapped") + ") + sync"
-                             if world == 1 else
-                             "per rank: bh_ctx_upload_models_async (48 MB over its own PCIe link) + bh_ray_pipeline_pass_to_host_frame (its bands stored "
-                             "straight into ONE page-locked host frame in POSIX shared memory, bh_host_frame) + host-side flags")},
+                    "frames_in_flight": 2, "frame_checksum": checksum, "both_host_frames_equal": e2e_lanes_equal,
+                    "path": ("two frames in flight, each on its own context / stream / host frame: "
+                             + ("bh_ctx_upload_models_async + bh_ray_pipeline_pass_to_host("
+                                + ("zero-copy: pixel stores land in the pinned host frame over PCIe during the pass" if args.e2e_chunks == 0
+                                   else f"{args.e2e_chunks} bands, D2H overlapped") + ") + sync + host read of the frame"
+                                if world == 1 else
+                                "per rank bh_ctx_upload_models_async (48 MB over its own PCIe link) + bh_ray_pipeline_pass_to_host_frame (its bands "
+                                "stored straight into ONE page-locked host frame in POSIX shared memory, bh_host_frame) + host-side flags")
+                             + "; frame k+1's upload runs under frame k's pass, buffers are reused only after the frame was finished and read")},
+            "e2e_serial": {"value": total["ray_steps"] * args.steps / e2e_serial_s / 1e6, "unit": UNIT, "ms_per_step": 1000.0 * e2e_serial_s / args.steps,
+                           "frames_in_flight": 1, "path": "same calls, one frame at a time: upload, pass, wait, read (round 1's e2e)"},
             "e2e_header_only": {"value": total["ray_steps"] * args.steps / e2e_hdr_s / 1e6, "unit": UNIT, "ms_per_step": 1000.0 * e2e_hdr_s / args.steps,
                                 "h2d_bytes_per_step": 16 * world + 196 * world, "d2h_bytes_per_step": int(W * H * 16),
+                                "frames_in_flight": 1,
                                 "path": "bh_ctx_set_model_header (position + visible, the fields the UI edits) instead of re-sending the 48 MB ModelUniform"},
             "gpu_launches": int(args.steps * (1 if world == 1 else 2)),
             "gpu_launches_note": "rank 0, timed region: trace_kernel per step" + ("" if world == 1 else " + the flag-wait kernel (other ranks: wait + trace + signal)"),
@@ -619,8 +664,12 @@ def run_ours(args):
             except Exception as ex:   # the oracle is a checker; its absence must not hide the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"unavailable: {ex}"}
         print(json.dumps(line))
-    if hframe is not None:
-        hframe.close()
+    for i, lane in enumerate(lanes):
+        if world > 1:
+            lane[2].close()
+        elif i > 0:
+            lane[3].close()
+    ctx_b.close()
     frame.close()
     if world > 1:
         dist.destroy_process_group()

@@ -263,16 +263,26 @@ class HostTiledFrame:
             self.host = HostFrame(ctx, self.name, nbytes, create=True)
         self._seq = 0
 
-    def render(self, camera, black_hole, details, stream=None):
-        """Every rank: enqueue, wait for the own kernel, publish.  Rank 0 returns once the whole frame is in host memory."""
+    def enqueue(self, camera, black_hole, details, stream=None):
+        """First half of render(): wait until rank 0 has let go of this buffer's previous frame, then enqueue the pass.  Returns
+        without waiting for the GPU, so the caller can enqueue the next frame on ANOTHER HostTiledFrame (its own context,
+        stream and host buffer) before finish()ing this one: two frames in flight, the upload of one under the pass of the other."""
         self._seq += 1
         if self.rank != 0 and self._seq > 1:
             self.host.wait(CONSUMED_SLOT, 1, self._seq - 1, WAIT_TIMEOUT_MS)        # rank 0 still reads the previous frame
         self.pipeline.pass_to_host_frame(camera, black_hole, details, self.host.ptr, stream)
+
+    def finish(self):
+        """Second half of render(): wait for the own kernel, publish; rank 0 returns once the whole frame is in host memory."""
         self.pipeline.sync()
         self.host.signal(self.rank, self._seq)
         if self.rank == 0 and self.world > 1:
             self.host.wait(1, self.world - 1, self._seq, WAIT_TIMEOUT_MS)
+
+    def render(self, camera, black_hole, details, stream=None):
+        """Every rank: enqueue, wait for the own kernel, publish.  Rank 0 returns once the whole frame is in host memory."""
+        self.enqueue(camera, black_hole, details, stream)
+        self.finish()
 
     def consumed(self):
         if self.rank == 0:
