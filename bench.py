@@ -296,6 +296,29 @@ def pyramid_block(ctx, P, U, torch, stream, reps=20):
             out[f"{name}_{mname}"] = {"ms_ray_levels_plus_sky": ms_ray, "ms_frame_with_post_chain": ms_all, "fps": 1000.0 / ms_all,
                                       "ray_steps": steps, "gsteps_per_s": steps / ms_ray / 1e6,
                                       "last_level_px_traced": last["px_traced"], "last_level_px_interp": last["px_interp"]}
+            # the same frame with TWO frames in flight (a renderer's usual double buffering: its own pyramid, post chain and stream per
+            # frame slot): frame k+1's latency-bound coarse levels run under frame k's last level.  Throughput, not latency.
+            pyr_b = P.RayPyramid(ctx, base=base)
+            chain_b = PostChain(ctx, pyr_b.sky)
+            stream_b = torch.cuda.Stream()
+            slots = ((pyr, chain, stream), (pyr_b, chain_b, stream_b))
+
+            def frames(n):
+                for k in range(n):
+                    py, ch, st = slots[k & 1]
+                    py.pass_(cam, hole, det, st)
+                    ch.pass_(st)
+            frames(4)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            stream_b.wait_event(e0)
+            frames(reps)
+            stream.wait_stream(stream_b)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            out[f"{name}_{mname}"]["ms_frame_with_post_chain_two_in_flight"] = e0.elapsed_time(e1) / reps
+            chain_b.close(); pyr_b.close()
             chain.close(); pyr.close()
     return out
 

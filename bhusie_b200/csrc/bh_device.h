@@ -57,6 +57,9 @@ struct PassParams {
     float disk_k;                    // 1.0021 * |hole.normal| (+inf when degenerate): fast disk-plane rejection, ray_impl.cuh hot_iteration
     float disk_far;                  // 1.001 * accretion_disk_outer (+inf when unusable): a segment that starts farther than
                                      // disk_far + 1.01 h from the hole cannot reach the annulus, ray_impl.cuh hot_iteration
+    int angle_fast;                  // classification (ray.wgsl:221-226): 1 when cos_hi / cos_lo bracket cos(angle_division_threshold)
+    float cos_hi, cos_lo;            // cosine above cos_hi: the angle is provably below the threshold; below cos_lo: provably not
+                                     // (classify_kernel evaluates the literal acos only in between), derive_pass_constants
 };
 
 // The two constants above, derived once per pass on the host.  They only ever SKIP a test whose outcome is then provably
@@ -72,6 +75,20 @@ inline void derive_pass_constants(PassParams &P)
     const float *b = P.hole.position;
     const float bmax = fmaxf(fmaxf(fabsf(b[0]), fabsf(b[1])), fabsf(b[2]));
     P.disk_far = (outer > 1e-3f && outer < 1e30f && bmax <= 64.0f * outer) ? 1.001f * outer : INFINITY;
+    // `acos(c) < thr` (angle_between, ray.wgsl:221-226) without the acos for all but the few c next to cos(thr).  The kernel's
+    // acos is atan2 in float64 rounded to f32: relative error < 7e-8.  So acos(c) < thr (1 - 1e-6) makes the rounded value < thr
+    // and acos(c) > thr (1 + 1e-6) makes it > thr (rounding is monotonic, and the margins are 8 f32 ulps wide); in terms of c,
+    // with cos decreasing on [0, pi]: c > cos(thr (1 - 1e-6)) and c < cos(thr (1 + 1e-6)).  One more f32 ulp either way covers
+    // the host's own cos().  For thr = 0.02 the two bounds are 3 f32 values apart.
+    const float thr = P.det.angle_division_threshold;
+    P.angle_fast = 0; P.cos_hi = INFINITY; P.cos_lo = -INFINITY;
+    if (thr >= 1e-3f && thr <= 3.0f) {
+        const double t = (double)thr;
+        const float hi = (float)cos(t * (1.0 - 1e-6)), lo = (float)cos(t * (1.0 + 1e-6));
+        P.cos_hi = nextafterf(nextafterf(hi, 2.0f), 2.0f);
+        P.cos_lo = nextafterf(nextafterf(lo, -2.0f), -2.0f);
+        P.angle_fast = 1;
+    }
 }
 
 struct SkyParams {

@@ -199,3 +199,32 @@ extern "C" int bh_host_warp_level(int mode, const void *camera, const void *hole
     if (stats9) memcpy(stats9, stats, sizeof stats);
     return 0;
 }
+
+// classify_kernel's angle test (cos_below_threshold) against its literal form acos(c) < thr: every f32 within `span` ulps of
+// cos(thr), plus a sweep of [-1, 1] and the special values.  Returns the number of disagreements (0 expected);
+// *n_literal = how many of the probed cosines <= 1 still needed the literal acos.
+extern "C" long bh_host_angle_shortcut_mismatches(float thr, int span, long *n_literal)
+{
+    using namespace bh;
+    PassParams P;
+    memset(&P, 0, sizeof P);
+    P.det.angle_division_threshold = thr;
+    derive_pass_constants(P);
+    long bad = 0, lit_n = 0;
+    auto probe = [&](float c) {
+        const bool fast = fus::cos_below_threshold(P, c);
+        const bool ref = detmath::acos_f(c) < thr;
+        if (fast != ref) ++bad;
+        if (c <= 1.0f && !(P.angle_fast && (c > P.cos_hi || c < P.cos_lo))) ++lit_n;     // (c > 1 and NaN are literal by design)
+    };
+    const float centre = (float)cos((double)thr);
+    float up = centre, dn = centre;
+    probe(centre);
+    for (int i = 0; i < span; ++i) { up = nextafterf(up, 4.0f); dn = nextafterf(dn, -4.0f); probe(up); probe(dn); }
+    for (int i = -100000; i <= 100000; ++i) probe((float)i * 1e-5f);
+    const float specials[] = { 1.0f, nextafterf(1.0f, 2.0f), nextafterf(1.0f, 0.0f), -1.0f, nextafterf(-1.0f, -2.0f), 0.0f, -0.0f,
+                               INFINITY, -INFINITY, NAN, 1e-30f, -1e-30f, 2.0f, -2.0f };
+    for (float c : specials) probe(c);
+    if (n_literal) *n_literal = lit_n;
+    return bad;
+}

@@ -185,6 +185,21 @@ def test_kernels_as_a_lockstep_warp_pyramid_and_sky(host_warp, oracle, small_sce
         prev_dev, prev_ora = rgba, ora.rgba
 
 
+@pytest.mark.parametrize("thr", [0.02, 0.001, 0.0123, 0.5, 1.5707963, 3.0, 0.0005, 3.1, 0.0, -1.0, float("nan")])
+def test_classification_angle_shortcut_equals_literal_acos(host_warp, thr):
+    """classify_kernel decides `acos(c) < angle_division_threshold` from c alone unless c is within a few ulps of cos(threshold)
+    (derive_pass_constants' cos_hi / cos_lo): same truth value as the literal acos for every probed cosine, and for thresholds in
+    the supported range nearly all of them are decided without it."""
+    host_warp.bh_host_angle_shortcut_mismatches.restype = C.c_long
+    n_lit = C.c_long(0)
+    bad = host_warp.bh_host_angle_shortcut_mismatches(C.c_float(thr), 4096, C.byref(n_lit))
+    assert bad == 0
+    if 1e-3 <= thr <= 0.6:
+        assert n_lit.value <= 64                     # the bracket around cos(thr): 3 f32 values at the reference's 0.02
+    elif not (1e-3 <= thr <= 3.0):
+        assert n_lit.value > 200000                  # outside the supported range the shortcut is off
+
+
 @pytest.mark.parametrize("tile_rows", [4, 2, 1])
 @pytest.mark.parametrize("case", ["default", "outside_sphere", "near_hole", "grazing_plane"])
 def test_kernels_as_a_lockstep_warp_single_level(host_warp, oracle, small_scene, small_oracle_scene, tile_rows, case):
