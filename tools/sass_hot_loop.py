@@ -57,6 +57,19 @@ def main():
             cur = []
     runs.append(cur)
     best = max(runs, key=lambda r: sum(opcode(t) in FP for _, t in r))
+    # the run may start in the loop's pre-header (the register moves that set up the first iteration): a backward branch that
+    # lands inside it marks where the loop body — what is executed per step — begins
+    lo, hi = int(best[0][0], 16), int(best[-1][0], 16)
+    heads = []
+    for addr, text in ins:
+        m = re.search(r"\bBRA(?:\.\w+)*\s+(?:\w+,\s*)?0x([0-9a-f]+)", text)
+        if m and lo < int(m.group(1), 16) <= hi and int(addr, 16) > hi:
+            heads.append(int(m.group(1), 16))
+    preheader = 0
+    if heads:
+        head = max(heads)
+        preheader = sum(1 for a, _ in best if int(a, 16) < head)
+        best = [(a, t) for a, t in best if int(a, 16) >= head]
     ops = collections.Counter(opcode(t) for _, t in best)
     units = sum(c * (2 if op in ("FFMA2", "FMUL2", "FADD2") else 1) for op, c in ops.items() if op in FP + ("IMAD", "HFMA2"))
     reads, prev = 0, {}
@@ -67,6 +80,8 @@ def main():
     print(f"quiet step: {best[0][0]}..{best[-1][0]}  {len(best)} instructions, {units} FMA-pipe units, {reads} register operand reads "
           f"({reads / 2:.0f} cycles at 2 per clock)")
     print("  " + "  ".join(f"{op} {c}" for op, c in ops.most_common()))
+    if preheader:
+        print(f"  ({preheader} instructions before the loop head, executed once per hot phase, are not counted)")
     if "--list" in sys.argv:
         for addr, text in best:
             print(f"    /*{addr}*/  {text}")
