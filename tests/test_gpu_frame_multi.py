@@ -154,6 +154,53 @@ def test_shared_host_frame_tiled_ranks(ctxs):
         P.HostFrame(ctxs[0], name, w * h * 16, create=False)   # unlinked by its owner
 
 
+def test_two_frames_in_flight_on_one_device(ctxs, small_scene):
+    """bench.py's e2e pattern: two frame slots on one device — each its own context (model buffer), stream and host frame —
+    with slot B's upload + pass enqueued before slot A's frame is finished and read.  Every frame of both slots equals the
+    plain device render (HostTiledFrame.enqueue / finish, bh_ctx_upload_models_async, bh_ray_pipeline_pass_to_host_frame)."""
+    import torch
+    from bhusie_b200.multi import HostTiledFrame
+    tex, blob, _ = small_scene
+    hole, det = U.BlackHole(), U.RayDetails(integration_method=1, model_count=1)
+    cams = [U.Camera(), U.Camera(position=(0.5, 0.2, -17.0)), U.Camera(position=(-1.0, 0.0, -21.0)), U.Camera(position=(0, 1.5, -19.0))]
+    w, h = 101, 47
+    single = P.RayPipeline(ctxs[0], w, h)
+    refs = []
+    for cam in cams:
+        single.pass_(cam, hole, det)
+        refs.append(single.read(aux=False)["rgba"].copy())
+    pinned = torch.from_numpy(np.ascontiguousarray(blob)).pin_memory()
+    slots = []
+    for i in range(2):
+        c = P.Context(ctxs[0].device)
+        c.set_textures(tex)
+        c.upload_models(blob)
+        slots.append((c, torch.cuda.Stream(), HostTiledFrame(c, w, h, 0, 1, name=f"/bhtest2_{os.getpid()}_{i}")))
+    pending = []
+    got = []
+    for k, cam in enumerate(cams):
+        c, st, hf = slots[k % 2]
+        c.upload_models_async(pinned.data_ptr(), pinned.numel(), st)
+        hf.enqueue(cam, hole, det, st)
+        pending.append((k, hf))
+        if len(pending) == 2:
+            j, f = pending.pop(0)
+            f.finish()
+            got.append((j, f.frame_array().copy()))
+            f.consumed()
+    while pending:
+        j, f = pending.pop(0)
+        f.finish()
+        got.append((j, f.frame_array().copy()))
+        f.consumed()
+    for j, frame in got:
+        assert np.array_equal(bits(frame), bits(refs[j])), f"frame {j}"
+    for c, _, hf in slots:
+        hf.close()
+        c.close()
+    single.close()
+
+
 def test_zero_copy_pass_marks_output_host_only(ctxs):
     """after bh_ray_pipeline_pass_to_host(n_chunks=0) the device buffer holds nothing of the pass, so read(),
     a child level and the sky pass must refuse it until a normal pass runs."""
