@@ -119,6 +119,7 @@ extern "C" int bh_host_kernel_pass(int mode, const void *camera, const void *hol
     for (int y = 0; y < h; ++y)
         for (int x = 0; x < w; ++x) {
             // what trace_kernel does per CTA / per item around trace_warp
+            if (mode == 0) lit::fill_unorm_table(0, 1); else fus::fill_unorm_table(0, 1);
             if (mode == 0) {
                 memset(lit::s_warp_stats, 0, sizeof lit::s_warp_stats);
                 if (P.det.model_count > 0) { memcpy(lit::s_model_top, models, 48); memcpy(lit::s_model_top + kTopHeaderBytes, models + kMuNodes, kTopNodes * 32); }
