@@ -267,7 +267,9 @@ def test_ragged_sizes_bit_exact(ctx_small, oracle, small_oracle_scene):
 
 
 # ------------------------------------------------------------------ adaptive grid + sky resolve
-@pytest.mark.parametrize("thr", [0.02, 0.08])
+# (0.02 is the reference's threshold, 0.08 makes most of the frame interpolate; the others sit on the edges of the range in which
+#  classify_kernel decides the angle test from the cosine — 1e-3 … 3 — or outside it: 0 and negative never interpolate, 3.5 > pi always does)
+@pytest.mark.parametrize("thr", [0.02, 0.08, 0.001, 0.0009, 0.7, 3.0, 3.5, 0.0, -0.5])
 def test_pyramid_and_sky_bit_exact(ctx_small, oracle, small_oracle_scene, thr):
     cam, hole = U.Camera(), U.BlackHole()
     det = U.RayDetails(integration_method=1, model_count=1, angle_division_threshold=thr)
