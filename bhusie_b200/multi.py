@@ -236,6 +236,20 @@ def _torch_stream(stream, device: int):
     return torch.cuda.ExternalStream(int(stream), device=device)
 
 
+def _create_host_frame(HostFrame, ctx, name: str, nbytes: int):
+    """(name used, error or None, HostFrame or None): the POSIX shared-memory object `name`, else a file of that name under the
+    temp directory (bh_host_frame_create maps either)."""
+    import os
+    import tempfile
+    errors = []
+    for candidate in (name, os.path.join(tempfile.gettempdir(), name.lstrip("/"))):
+        try:
+            return candidate, None, HostFrame(ctx, candidate, nbytes, create=True)
+        except Exception as ex:              # noqa: BLE001 - the message travels to the other ranks
+            errors.append(f"{candidate}: {ex}")
+    return None, "; ".join(errors), None
+
+
 class HostTiledFrame:
     """End-to-end frame on `world` ranks with HOST buffers: one page-locked frame in POSIX shared memory that every rank
     maps (bh_host_frame); each rank's ray kernel stores its cyclic bands straight into it over its own PCIe link — no
@@ -253,14 +267,36 @@ class HostTiledFrame:
         nbytes = width * height * 16
         if world > 1:
             import torch.distributed as dist
+            # Rank 0 creates the segment and tells the others its name — or why it could not — so that every rank attaches or
+            # raises together (a rank that raised alone would leave the others waiting in a collective).  A /dev/shm too small
+            # for the frame (container default: 64 MB) falls back to a file under the temp directory.
+            verdict = [None, None]
             if rank == 0:
-                self.host = HostFrame(ctx, self.name, nbytes, create=True)
-            dist.barrier()
-            if rank != 0:
-                self.host = HostFrame(ctx, self.name, nbytes, create=False)
-            dist.barrier()
+                verdict = list(_create_host_frame(HostFrame, ctx, self.name, nbytes))
+                self.host = verdict.pop()
+            dist.broadcast_object_list(verdict, src=0)
+            chosen, error = verdict[0], verdict[1]
+            attach_error = None
+            if error is None and rank != 0:
+                try:
+                    self.host = HostFrame(ctx, chosen, nbytes, create=False)
+                except Exception as ex:      # noqa: BLE001 - reported to every rank below
+                    attach_error = f"rank {rank}: {ex}"
+            errors = [None] * world
+            dist.all_gather_object(errors, error or attach_error)
+            errors = [e for e in errors if e]
+            if errors:
+                if getattr(self, "host", None) is not None:
+                    self.host.close()
+                self.pipeline.close()
+                raise RuntimeError("HostTiledFrame: " + "; ".join(errors))
+            self.name = chosen
         else:
-            self.host = HostFrame(ctx, self.name, nbytes, create=True)
+            chosen, error, self.host = _create_host_frame(HostFrame, ctx, self.name, nbytes)
+            if error is not None:
+                self.pipeline.close()
+                raise RuntimeError("HostTiledFrame: " + error)
+            self.name = chosen
         self._seq = 0
 
     def enqueue(self, camera, black_hole, details, stream=None):
