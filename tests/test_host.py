@@ -234,3 +234,25 @@ def test_model_validate_on_the_host():
         assert e.value.code == -22
     empty, _ = P.model_from_arrays(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32), np.zeros((0, 6), np.int32))
     P.validate_model(empty)
+
+
+def test_host_frame_name_falls_back_to_temp_dir():
+    """HostTiledFrame's rank 0 tries the POSIX shared-memory name first and a file under the temp directory second, and hands the
+    other ranks either the name that worked or every reason why none did (bhusie_b200/multi.py::_create_host_frame)."""
+    import tempfile
+    from bhusie_b200.multi import _create_host_frame
+
+    class OnlyFiles:
+        def __init__(self, ctx, name, nbytes, create):
+            if name.count("/") < 2:
+                raise OSError("No space left on device")
+            self.name = name
+
+    class Nothing:
+        def __init__(self, ctx, name, nbytes, create):
+            raise OSError(f"cannot map {name}")
+
+    name, err, hf = _create_host_frame(OnlyFiles, None, "/bhframe_test", 1 << 20)
+    assert err is None and name == os.path.join(tempfile.gettempdir(), "bhframe_test") and hf.name == name
+    name, err, hf = _create_host_frame(Nothing, None, "/bhframe_test", 1 << 20)
+    assert name is None and hf is None and "/bhframe_test" in err and tempfile.gettempdir() in err
