@@ -62,16 +62,17 @@ constexpr int kTopNodes = 256;
 constexpr int kTopHeaderBytes = 64;                       // 48 used, padded to keep the nodes 16-byte aligned
 constexpr int kTopBytes = kTopHeaderBytes + kTopNodes * 32;
 
-// Resident CTAs per SM (tuning: -DBH_OCC_RK=n -DBH_OCC_EULER=n).  Measured at 4K (tools/gpu_time_modes.py): the Cash-Karp
+// Resident CTAs per SM (tuning: -DBH_OCC_RK=n -DBH_OCC_EULER=n).  Measured at 4K (tools/gpu_c3_probe.py): the Cash-Karp
 // kernel is fastest spill-free at 4 CTAs/SM (14.7 ms; 5: 15.1, 6: 15.3): its hot loop runs at ~70 % of three coincident
-// limits (issue slots, FMA pipe, register operand bandwidth), so extra warps buy nothing once spills appear.  Euler is flat
-// from 4 to 6 (8.61 / 8.58 / 8.62 ms) and loses at 8 (9.36 ms, spills).  A value other than 4 for Euler adds a second build
-// that launch_trace_mode uses on frames that saturate the GPU.
+// limits (issue slots, FMA pipe, register operand bandwidth), so extra warps buy nothing once spills appear.  Euler — a short
+// dependent chain per step, latency- rather than pipe-bound — gains from a fifth CTA since the kernel shrank in round 2:
+// 7.72 -> 7.47 ms (254 -> 263 G ray-steps/s) at 5, 7.70 at 6 (round 1: flat from 4 to 6, 9.36 ms at 8 with spills).  A value
+// other than 4 for Euler adds a second build that launch_trace_mode uses on tile-mode frames that saturate the GPU.
 #ifndef BH_OCC_RK
 #define BH_OCC_RK 4
 #endif
 #ifndef BH_OCC_EULER
-#define BH_OCC_EULER 4
+#define BH_OCC_EULER 5
 #endif
 // lanes of a 32-ray warp that must wait for disk shading before the hot phase is interrupted for them (1 = serve every crossing at
 // once).  Reference frame, RK: 4 -> 2.72 ms, 8 -> 2.59, 16 -> 2.53, 24 -> 2.46, 32 -> 2.43 (profiles/r2_10_*, r2_11_*_quick.json): in

@@ -116,6 +116,18 @@ def test_c2i_full_frame(ctx, scene, oracle):
     rp.close()
 
 
+def test_euler_full_frame_with_mesh(ctx, scene, oracle):
+    """1920x1080, the reference's default Euler integrator, disk + relativity sphere + lucy.obj, every pixel traced in tile mode:
+    a launch large enough for launch_trace_mode to pick the Euler build with 5 resident CTAs per SM (BH_OCC_EULER) — every
+    pixel, hit index, step count and counter against the mode's oracle flavour."""
+    _, _, osc = scene
+    cam, hole, det = U.Camera(), U.BlackHole(), U.RayDetails(integration_method=0, model_count=1)
+    rp = P.RayPipeline(ctx, 1920, 1080, aux=P.AUX_HIT | P.AUX_STEPS)
+    rp.pass_(cam, hole, det)
+    check_frame(oracle, osc, ctx, "Euler_1920x1080_mesh", rp.read(), rp.stats(), 1920, 1080, cam.uniform(), hole.uniform(), det.uniform())
+    rp.close()
+
+
 @pytest.mark.parametrize("method", [1, 0])
 def test_c2ii_reference_pyramid_all_levels(ctx, scene, oracle, method):
     """BASELINE configs[1], sub-run (ii): the reference's own frame — four levels up to 1918x1081 (mod.rs:177-206) and the
