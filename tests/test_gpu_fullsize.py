@@ -166,6 +166,21 @@ def test_c3_full_frame(ctx, scene, oracle):
     rp.close()
 
 
+@pytest.mark.parametrize("method", [1, 0])
+def test_c3_camera_outside_the_sphere_full_frame(ctx, scene, oracle, method):
+    """SURVEY §8(d) C3's second camera, (0,0,-45), outside R_rel = 20: by Q3 every Cash-Karp ray ping-pongs between one step and
+    one flat-space iteration ~170 times before it is inside (the exit-in-the-tail path and the sphere-bounded BVH walk at full
+    scale); Euler enters once.  Whole 3840x2160 frame: pixels, hit indices, step counts and counters against the mode's flavour."""
+    _, _, osc = scene
+    cam, hole, det = U.Camera(position=(0.0, 0.0, -45.0)), U.BlackHole(), U.RayDetails(integration_method=method, model_count=1)
+    rp = P.RayPipeline(ctx, 3840, 2160, aux=P.AUX_HIT | P.AUX_STEPS)
+    rp.pass_(cam, hole, det)
+    dev, st = rp.read(), rp.stats()
+    check_frame(oracle, osc, ctx, f"C3_cam45_m{method}_3840x2160", dev, st, 3840, 2160, cam.uniform(), hole.uniform(), det.uniform())
+    assert (dev["hit"] >= 0).sum() > 1000
+    rp.close()
+
+
 def test_c4_8k_as_eight_tiled_ranks(ctx, scene, oracle):
     """BASELINE configs[3]: 7680x4320, the frame cut into cyclic 8-row bands over 8 ranks — here the 8 ranks run one after
     the other on one device, each into its compact band buffer; 5 rows of every rank (40 in all) are compared with the
